@@ -1,0 +1,86 @@
+// dp_gemm.cuh -- parameter block of the tcgen05 implicit-GEMM convolution / GEMM kernel.
+//
+// One kernel family covers every dense contraction of the three score-model UNets
+// (reference call sites: 3x3 conv  score_sde/models/layers.py:118-124, guided_diffusion/unet.py:193,219,
+//  ddpm/unet_ddpm.py:95-108; 1x1 conv / NIN layers.py:100-105,546-555, unet.py:230, unet_ddpm.py:117-121;
+//  stride-2 conv unet_ddpm.py:63-82; attention matmuls layerspp.py:75-91, unet.py:345-362,
+//  unet_ddpm.py:172-197; time-embedding Linears ncsnpp.py:246-255, unet.py:478-483):
+//
+//   D[M, N] = sum_seg sum_tap sum_c  A_seg[pixel(m) + tap, c] * Wt[n, k(seg, tap, c)]
+//
+// A operand: bf16 NHWC activations read through 4-D TMA tensor maps (C, W, H, B); the 3x3 halo and
+// the zero padding come from TMA out-of-bounds zero fill, a stride-2 conv from the map's element
+// strides. Up to two K segments (main 3x3 input + fused 1x1 shortcut input).
+// B operand: bf16 weights [N, Ktotal] (K contiguous) through a 2-D tensor map.
+// Accumulation: fp32 in TMEM (tcgen05.mma kind::f16), 128 x BN tile per CTA, double-buffered.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace dp {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
+
+struct GemmASeg {
+  CUtensorMap tmap;  // (C, W, H, B) bf16, box (64, bw, bh, bn), SWIZZLE_128B
+  int taps;          // 1 or 9
+  int kchunks;       // C / 64
+  int stride;        // coordinate multiplier (2 for the stride-2 downsample conv)
+  int pad;           // subtracted from the tap offset (1 for 'same' 3x3, else 0)
+};
+
+struct GemmParams {
+  GemmASeg a[2];
+  CUtensorMap tmap_b;  // (Ktotal, Nrows) bf16, box (64, BN), SWIZZLE_128B
+  int nseg;
+  // output pixel grid of one batch entry (plain GEMM: H = 1, W = M)
+  int H, W, bw, bh;
+  int tiles_w, tiles_per_img;  // tiles_per_img = tiles_w * tiles_h, 0 if several images share a tile
+  int imgs_per_tile;           // 128 / (H*W) when H*W < 128, else 1
+  int M;                       // valid rows per batch entry
+  int N;                       // valid columns
+  int m_tiles, n_tiles, batch;
+  int a_batch_rows;  // added to the W coordinate of A per batch entry (batched GEMM)
+  int b_batch_rows;  // added to the row coordinate of B per batch entry
+  int num_stages;
+  // ---- epilogue ----
+  const float* bias;  // [N] (or [M] if bias_along_m)
+  int bias_along_m;
+  const float* rowvec;  // per-sample additive vector: rowvec[(row >> rowvec_shift) * rowvec_ld + col]
+  int rowvec_ld, rowvec_shift;
+  const float* rowscale;  // out *= 1 / rowscale[b*M + row]
+  const float* resid;     // fp32 residual, same addressing as out_f32
+  float alpha;            // final scale
+  int silu;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  long long ldc;               // row stride (elements) of out / resid
+  long long out_batch_stride;  // elements
+  float* stats;                // [segments][N][2] per-channel (sum, sumsq) partials, or null
+  int stat_nseg;               // row segments per tile: 1 (HW>=128), 2 (HW=64), 8 (HW=16)
+  // ---- softmax epilogue (kSoftmax kernels): P = exp(scale*(S - rowmax)) (bf16), rowsum out ----
+  float softmax_scale;
+  float* rowsum_out;  // [batch*M]
+};
+
+// Launches the persistent kernel (grid = min(tiles, num_sms)). BN in {128, 256}.
+// Returns cudaError_t as int.
+int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream);
+// Dynamic shared memory needed for (bn, stages); and the max stage count that fits.
+size_t gemm_smem_bytes(int bn, int stages);
+int gemm_max_stages(int bn);
+// One-time cudaFuncSetAttribute for all instantiations.
+int gemm_init();
+
+// Tile box of the output pixel grid: full rows when W < 128, else 128-pixel row segments.
+struct TileBox {
+  int bw, bh, bn;
+};
+TileBox gemm_tile_box(int H, int W);
+// Fills H/W/bw/bh/tiles_*/imgs_per_tile/M/N/m_tiles/n_tiles/stat_nseg/num_stages for an output grid of
+// B images of H x W pixels (plain GEMM: B = 1, H = 1, W = rows) and N output columns.
+void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn);
+
+}  // namespace dp

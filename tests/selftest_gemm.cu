@@ -1,0 +1,333 @@
+// selftest_gemm.cu -- standalone on-GPU check of the tcgen05 implicit-GEMM kernel against a plain
+// host loop (fp32 accumulation of the same bf16-rounded operands). Built by tests/build_selftest.sh,
+// run by tests/test_gpu_kernels.py (-m gpu). Exit code 0 = all cases within tolerance.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../diffpure_b200/csrc/dp_gemm.cuh"
+#include "../diffpure_b200/csrc/dp_tmap.h"
+
+using dp::GemmParams;
+
+#define CK(x)                                                                             \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) {                                                              \
+      printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      exit(2);                                                                            \
+    }                                                                                     \
+  } while (0)
+
+static std::mt19937 rng(1234);
+static float frand(float s = 1.f) {
+  std::uniform_real_distribution<float> d(-s, s);
+  return d(rng);
+}
+static float bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <class T>
+T* dev(const std::vector<T>& h) {
+  T* d;
+  CK(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+static std::vector<__nv_bfloat16> tobf(const std::vector<float>& v) {
+  std::vector<__nv_bfloat16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+  return o;
+}
+
+struct ConvCase {
+  const char* name;
+  int B, H, W;        // output grid
+  int C0, taps0;      // segment 0 (input spatial = output spatial * stride)
+  int C1;             // segment 1 (1x1), 0 = none
+  int N, bn;
+  int stride;         // 1 or 2 (stride 2: pad right/bottom only, taps 9)
+  bool bias, rowvec, resid, silu, stats, out_bf16;
+  float alpha;
+};
+
+static int num_sms = 148;
+static int failures = 0;
+
+static void run_conv(const ConvCase& cs) {
+  const int B = cs.B, H = cs.H, W = cs.W, N = cs.N;
+  const int Hin = H * cs.stride, Win = W * cs.stride;
+  const int K0 = cs.taps0 * cs.C0, Kt = K0 + cs.C1;
+  const int M = B * H * W;
+  std::vector<float> a0((size_t)B * Hin * Win * cs.C0), a1((size_t)M * (cs.C1 ? cs.C1 : 1)), w((size_t)N * Kt);
+  for (auto& v : a0) v = bf(frand());
+  for (auto& v : a1) v = bf(frand());
+  const float ws = 1.0f / sqrtf((float)Kt);
+  for (auto& v : w) v = bf(frand(ws * 1.7f));
+  std::vector<float> bias(N), rowvec((size_t)B * N), resid((size_t)M * N);
+  for (auto& v : bias) v = frand();
+  for (auto& v : rowvec) v = frand();
+  for (auto& v : resid) v = frand();
+
+  auto a0b = tobf(a0);
+  auto a1b = tobf(a1);
+  auto wb = tobf(w);
+  __nv_bfloat16* d_a0 = dev(a0b);
+  __nv_bfloat16* d_a1 = dev(a1b);
+  __nv_bfloat16* d_w = dev(wb);
+  float* d_bias = dev(bias);
+  float* d_rowvec = dev(rowvec);
+  float* d_resid = dev(resid);
+  float *d_out, *d_stats;
+  __nv_bfloat16* d_outb;
+  CK(cudaMalloc(&d_out, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_outb, (size_t)M * N * 2));
+  CK(cudaMemset(d_out, 0xff, (size_t)M * N * 4));
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = 1;
+  dp::gemm_fill_geometry(p, B, H, W, N, cs.bn);
+  const int nsegs_total = p.m_tiles * p.stat_nseg;
+  CK(cudaMalloc(&d_stats, (size_t)nsegs_total * N * 2 * 4));
+  CK(cudaMemset(d_stats, 0, (size_t)nsegs_total * N * 2 * 4));
+  const dp::TileBox tb = dp::gemm_tile_box(H, W);
+  std::string err;
+  if (dp::make_act_tmap(&p.a[0].tmap, d_a0, cs.C0, cs.C0, Win, Hin, B, tb.bw, tb.bh, tb.bn, cs.stride, &err)) {
+    printf("[%s] tmap a0: %s\n", cs.name, err.c_str());
+    failures++;
+    return;
+  }
+  p.a[0].taps = cs.taps0;
+  p.a[0].kchunks = cs.C0 / 64;
+  p.a[0].stride = cs.stride;
+  p.a[0].pad = (cs.taps0 == 9 && cs.stride == 1) ? 1 : 0;
+  p.nseg = 1;
+  if (cs.C1) {
+    if (dp::make_act_tmap(&p.a[1].tmap, d_a1, cs.C1, cs.C1, W, H, B, tb.bw, tb.bh, tb.bn, 1, &err)) {
+      printf("[%s] tmap a1: %s\n", cs.name, err.c_str());
+      failures++;
+      return;
+    }
+    p.a[1].taps = 1;
+    p.a[1].kchunks = cs.C1 / 64;
+    p.a[1].stride = 1;
+    p.a[1].pad = 0;
+    p.nseg = 2;
+  }
+  if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, cs.bn, &err)) {
+    printf("[%s] tmap b: %s\n", cs.name, err.c_str());
+    failures++;
+    return;
+  }
+  p.bias = cs.bias ? d_bias : nullptr;
+  p.rowvec = cs.rowvec ? d_rowvec : nullptr;
+  p.rowvec_ld = N;
+  int sh = 0;
+  while ((1 << sh) < H * W) ++sh;
+  p.rowvec_shift = sh;
+  p.resid = cs.resid ? d_resid : nullptr;
+  p.alpha = cs.alpha;
+  p.silu = cs.silu;
+  p.out_f32 = d_out;
+  p.out_bf16 = cs.out_bf16 ? d_outb : nullptr;
+  p.ldc = N;
+  p.out_batch_stride = 0;
+  p.stats = cs.stats ? d_stats : nullptr;
+
+  int e = dp::launch_gemm(p, cs.bn, false, num_sms, 0);
+  cudaError_t se = cudaDeviceSynchronize();
+  if (e || se != cudaSuccess) {
+    printf("[%s] launch/sync error %d / %s\n", cs.name, e, cudaGetErrorString(se));
+    failures++;
+    exit(3);
+  }
+  std::vector<float> out((size_t)M * N), stats((size_t)nsegs_total * N * 2);
+  std::vector<__nv_bfloat16> outb((size_t)M * N);
+  CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(outb.data(), d_outb, outb.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(stats.data(), d_stats, stats.size() * 4, cudaMemcpyDeviceToHost));
+
+  // host reference
+  double maxerr = 0, maxref = 0, maxerr_b = 0;
+  std::vector<double> rs((size_t)nsegs_total * N * 2, 0.0);
+  const int hw = H * W;
+  const int seg_rows = hw >= 128 ? 128 : hw;
+  for (int b = 0; b < B; ++b)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const size_t row = ((size_t)b * H + y) * W + x;
+        for (int n = 0; n < N; ++n) {
+          float acc = 0.f;
+          const float* wr = &w[(size_t)n * Kt];
+          for (int t = 0; t < cs.taps0; ++t) {
+            const int ky = cs.taps0 == 9 ? t / 3 : 0, kx = cs.taps0 == 9 ? t % 3 : 0;
+            const int pad = (cs.taps0 == 9 && cs.stride == 1) ? 1 : 0;
+            const int yy = y * cs.stride + ky - pad, xx = x * cs.stride + kx - pad;
+            if (yy < 0 || yy >= Hin || xx < 0 || xx >= Win) continue;
+            const float* ar = &a0[(((size_t)b * Hin + yy) * Win + xx) * cs.C0];
+            const float* wt = wr + (size_t)t * cs.C0;
+            for (int c = 0; c < cs.C0; ++c) acc += ar[c] * wt[c];
+          }
+          if (cs.C1) {
+            const float* ar = &a1[row * cs.C1];
+            const float* wt = wr + K0;
+            for (int c = 0; c < cs.C1; ++c) acc += ar[c] * wt[c];
+          }
+          float v = acc;
+          if (cs.bias) v += bias[n];
+          if (cs.rowvec) v += rowvec[(size_t)b * N + n];
+          if (cs.silu) v = v / (1.f + expf(-v));
+          if (cs.resid) v += resid[row * N + n];
+          v *= cs.alpha;
+          const double d = fabs((double)v - out[row * N + n]);
+          if (d > maxerr) maxerr = d;
+          if (fabs(v) > maxref) maxref = fabs(v);
+          if (cs.out_bf16) {
+            const double db = fabs((double)v - __bfloat162float(outb[row * N + n]));
+            if (db > maxerr_b) maxerr_b = db;
+          }
+          const size_t sg = row / seg_rows;
+          rs[(sg * N + n) * 2 + 0] += v;
+          rs[(sg * N + n) * 2 + 1] += (double)v * v;
+        }
+      }
+  double maxs = 0, maxsref = 0;
+  if (cs.stats) {
+    const size_t nvalid = (size_t)((M + seg_rows - 1) / seg_rows) * N * 2;
+    for (size_t i = 0; i < nvalid; ++i) {
+      maxs = fmax(maxs, fabs(rs[i] - stats[i]));
+      maxsref = fmax(maxsref, fabs(rs[i]));
+    }
+  }
+  const bool ok = maxerr <= 2e-3 * fmax(1.0, maxref) && (!cs.out_bf16 || maxerr_b <= 1e-2 * fmax(1.0, maxref)) &&
+                  (!cs.stats || maxs <= 1e-3 * fmax(1.0, maxsref));
+  printf("[%s] %s  max|err|=%.3e (max|ref|=%.3f) bf16out err=%.3e stats err=%.3e (ref %.2f)\n", cs.name,
+         ok ? "OK  " : "FAIL", maxerr, maxref, maxerr_b, maxs, maxsref);
+  if (!ok) failures++;
+  cudaFree(d_a0); cudaFree(d_a1); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_rowvec); cudaFree(d_resid);
+  cudaFree(d_out); cudaFree(d_outb); cudaFree(d_stats);
+}
+
+// Batched attention-style GEMMs: S = softmax-numerator(Q K^T) then O = P V^T-layout.
+static void run_attention(int Bt, int T, int C, int bn_s) {
+  // qk: [Bt*T, 2C] bf16 (q | k); vt: [Bt, C, T] bf16
+  std::vector<float> qk((size_t)Bt * T * 2 * C), vt((size_t)Bt * C * T);
+  for (auto& v : qk) v = bf(frand(1.5f));
+  for (auto& v : vt) v = bf(frand());
+  auto qkb = tobf(qk);
+  auto vtb = tobf(vt);
+  __nv_bfloat16* d_qk = dev(qkb);
+  __nv_bfloat16* d_vt = dev(vtb);
+  __nv_bfloat16* d_p;
+  float *d_rs, *d_o;
+  CK(cudaMalloc(&d_p, (size_t)Bt * T * T * 2));
+  CK(cudaMalloc(&d_rs, (size_t)Bt * T * 4));
+  CK(cudaMalloc(&d_o, (size_t)Bt * T * C * 4));
+  const float scale = 1.0f / sqrtf((float)C);
+  std::string err;
+  {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = Bt;
+    dp::gemm_fill_geometry(p, 1, 1, T, T, bn_s);
+    // A = q rows: matrix [Bt*T, C] with pitch 2C ; as 4-D (C, rows, 1, 1)
+    if (dp::make_act_tmap(&p.a[0].tmap, d_qk, C, 2 * C, Bt * T, 1, 1, 128, 1, 1, 1, &err)) { printf("tmap q: %s\n", err.c_str()); failures++; return; }
+    p.a[0].taps = 1; p.a[0].kchunks = C / 64; p.a[0].stride = 1; p.a[0].pad = 0; p.nseg = 1;
+    p.a_batch_rows = T;
+    if (dp::make_mat_tmap(&p.tmap_b, d_qk + C, C, (long long)Bt * T, 2 * C, bn_s, &err)) { printf("tmap k: %s\n", err.c_str()); failures++; return; }
+    p.b_batch_rows = T;
+    p.out_bf16 = d_p; p.ldc = T; p.out_batch_stride = (long long)T * T;
+    p.softmax_scale = scale; p.rowsum_out = d_rs; p.alpha = 1.f;
+    int e = dp::launch_gemm(p, bn_s, true, num_sms, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    if (e || se != cudaSuccess) { printf("[attn S] launch/sync error %d / %s\n", e, cudaGetErrorString(se)); exit(3); }
+  }
+  {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = Bt;
+    const int bn_o = (C % 256 == 0) ? 256 : 128;
+    dp::gemm_fill_geometry(p, 1, 1, T, C, bn_o);
+    if (dp::make_act_tmap(&p.a[0].tmap, d_p, T, T, Bt * T, 1, 1, 128, 1, 1, 1, &err)) { printf("tmap p: %s\n", err.c_str()); failures++; return; }
+    p.a[0].taps = 1; p.a[0].kchunks = T / 64; p.a[0].stride = 1; p.a[0].pad = 0; p.nseg = 1;
+    p.a_batch_rows = T;
+    if (dp::make_mat_tmap(&p.tmap_b, d_vt, T, (long long)Bt * C, T, bn_o, &err)) { printf("tmap vt: %s\n", err.c_str()); failures++; return; }
+    p.b_batch_rows = C;
+    p.out_f32 = d_o; p.ldc = C; p.out_batch_stride = (long long)T * C;
+    p.rowscale = d_rs; p.alpha = 1.f;
+    int e = dp::launch_gemm(p, bn_o, false, num_sms, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    if (e || se != cudaSuccess) { printf("[attn O] launch/sync error %d / %s\n", e, cudaGetErrorString(se)); exit(3); }
+  }
+  std::vector<float> o((size_t)Bt * T * C);
+  CK(cudaMemcpy(o.data(), d_o, o.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0;
+  std::vector<float> s(T), pr(T);
+  for (int b = 0; b < Bt; ++b)
+    for (int i = 0; i < T; ++i) {
+      float mx = -1e30f;
+      for (int j = 0; j < T; ++j) {
+        float acc = 0;
+        for (int c = 0; c < C; ++c) acc += qk[((size_t)b * T + i) * 2 * C + c] * qk[((size_t)b * T + j) * 2 * C + C + c];
+        s[j] = acc;
+        mx = fmaxf(mx, acc);
+      }
+      float sum = 0;
+      for (int j = 0; j < T; ++j) { pr[j] = bf(expf((s[j] - mx) * scale)); sum += pr[j]; }
+      for (int c = 0; c < C; ++c) {
+        float acc = 0;
+        for (int j = 0; j < T; ++j) acc += pr[j] * vt[((size_t)b * C + c) * T + j];
+        const float v = acc / sum;
+        maxerr = fmax(maxerr, fabs((double)v - o[((size_t)b * T + i) * C + c]));
+        maxref = fmax(maxref, fabs(v));
+      }
+    }
+  const bool ok = maxerr <= 5e-3 * fmax(1.0, maxref);
+  printf("[attention Bt=%d T=%d C=%d] %s max|err|=%.3e (max|ref|=%.3f)\n", Bt, T, C, ok ? "OK  " : "FAIL", maxerr, maxref);
+  if (!ok) failures++;
+  cudaFree(d_qk); cudaFree(d_vt); cudaFree(d_p); cudaFree(d_rs); cudaFree(d_o);
+}
+
+int main(int argc, char** argv) {
+  int devid = 0;
+  CK(cudaSetDevice(devid));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, devid));
+  num_sms = prop.multiProcessorCount;
+  printf("device %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, num_sms);
+  int e = dp::gemm_init();
+  if (e) { printf("gemm_init failed %d\n", e); return 2; }
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+
+  const ConvCase cases[] = {
+      // name                      B  H   W   C0  taps C1   N   bn  st  bias  rowv  resid silu  stats bf16  alpha
+      {"gemm 512x128x256",         1, 1, 512, 256, 1,  0, 128, 128, 1, false,false,false,false,false,false, 1.f},
+      {"gemm 300x256x512 bn256",   1, 1, 300, 512, 1,  0, 256, 256, 1, true, false,false,false,false,true,  1.f},
+      {"gemm M=16 (temb-like)",    1, 1, 16,  128, 1,  0, 512, 256, 1, true, false,false,true, false,true,  1.f},
+      {"conv3x3 32x32 128->128",   2, 32, 32, 128, 9,  0, 128, 128, 1, true, true, true, false,true, false, 0.70710678f},
+      {"conv3x3 16x16 256->256",   4, 16, 16, 256, 9,  0, 256, 256, 1, true, true, false,false,true, true,  1.f},
+      {"conv3x3 8x8 256->256",     5, 8,  8,  256, 9,  0, 256, 128, 1, true, true, true, false,true, false, 0.70710678f},
+      {"conv3x3 4x4 256->256",     11, 4, 4,  256, 9,  0, 256, 256, 1, true, true, true, false,true, false, 0.70710678f},
+      {"conv3x3+1x1 16x16",        3, 16, 16, 256, 9, 512, 256, 256, 1, true, false,false,false,true, false, 0.70710678f},
+      {"conv1x1 32x32 256->128",   2, 32, 32, 256, 1,  0, 128, 128, 1, true, false,true, false,false,false, 1.f},
+      {"conv3x3 s2 32->16 128",    2, 16, 16, 128, 9,  0, 128, 128, 2, true, false,false,false,true, false, 1.f},
+      {"conv3x3 256x256 64->128",  1, 256,256, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f},
+      {"conv3x3 s2 256->128 64",   1, 128,128, 64, 9,  0, 128, 128, 2, true, false,false,false,false,false, 1.f},
+  };
+  const int ncases = sizeof(cases) / sizeof(cases[0]);
+  for (int i = 0; i < ncases; ++i) {
+    if (quick && i >= 4) break;
+    run_conv(cases[i]);
+  }
+  run_attention(3, 256, 256, 256);
+  if (!quick) run_attention(2, 128, 512, 128);
+  printf("selftest_gemm: %d failure(s)\n", failures);
+  return failures ? 1 : 0;
+}
