@@ -1,0 +1,565 @@
+// dp_elem.cu -- bandwidth-bound kernels around the tcgen05 GEMMs (sm_100a): GroupNorm apply (+SiLU, FiLM,
+// resample, concat) producing the bf16 GEMM operands, GroupNorm statistics, timestep embedding, the 3->C input
+// conv, the C->3|6 output conv fused with the per-step SDE / DDPM update, short-sequence attention, layout
+// conversion. All activations are NHWC; vector width is 8 channels (32 B fp32 in, 16 B bf16 out).
+#include "dp_elem.cuh"
+
+#include <cstdio>
+
+namespace dp {
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& a, float& b) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  a = __bfloat162float(t.x);
+  b = __bfloat162float(t.y);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based normals (Philox4x32-10 + Box-Muller)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ static inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                                    uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+  const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+  const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+  const uint32_t n1 = static_cast<uint32_t>(p1);
+  const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+  const uint32_t n3 = static_cast<uint32_t>(p0);
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__host__ __device__ float dp_normal(unsigned long long seed, unsigned long long sample, unsigned int stream,
+                                    unsigned int pixel, int c) {
+  uint32_t c0 = static_cast<uint32_t>(sample), c1 = static_cast<uint32_t>(sample >> 32), c2 = stream, c3 = pixel;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const uint32_t a = (c < 2) ? c0 : c2, b = (c < 2) ? c1 : c3;
+  const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * logf(u1));
+  const float ang = 6.283185307179586f * u2;
+  return (c == 1) ? rad * sinf(ang) : rad * cosf(ang);
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_kernel(EmbedParams p) {
+  const int b = blockIdx.x;
+  const int half = p.dim / 2;
+  const float cond = p.cond_per_sample ? p.cond_per_sample[b] : p.tables.cond[*p.tables.step];
+  const float coef = -logf(10000.0f) / static_cast<float>(p.half_minus_1 ? half - 1 : half);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float freq = expf(static_cast<float>(i) * coef);
+    const float arg = cond * freq;
+    const float s = sinf(arg), c = cosf(arg);
+    p.out[static_cast<size_t>(b) * p.dim + i] = __float2bfloat16_rn(p.cos_first ? c : s);
+    p.out[static_cast<size_t>(b) * p.dim + half + i] = __float2bfloat16_rn(p.cos_first ? s : c);
+  }
+}
+
+int launch_embed(const EmbedParams& p, cudaStream_t s) {
+  embed_kernel<<<p.B, 128, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, int ppc) {
+  extern __shared__ float sm[];
+  const int C = p.C0 + p.C1;
+  const int G = p.groups;
+  float* sc = sm;
+  float* sh = sm + C;
+  float* gs = sm + 2 * C;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int HW = p.H * p.W;
+
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float* st;
+    int P, Cx, cl;
+    if (c < p.C0) { st = p.stats0; P = p.P0; Cx = p.C0; cl = c; }
+    else          { st = p.stats1; P = p.P1; Cx = p.C1; cl = c - p.C0; }
+    st += (static_cast<size_t>(b) * P * Cx + cl) * 2;
+    float s = 0.f, q = 0.f;
+    for (int pp = 0; pp < P; ++pp) {
+      s += st[static_cast<size_t>(pp) * Cx * 2];
+      q += st[static_cast<size_t>(pp) * Cx * 2 + 1];
+    }
+    sc[c] = s;
+    sh[c] = q;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = tid; g < G; g += blockDim.x) {
+    double S = 0.0, Q = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      S += sc[g * cpg + j];
+      Q += sh[g * cpg + j];
+    }
+    const double n = static_cast<double>(cpg) * HW;
+    const double mean = S / n;
+    double var = Q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gs[2 * g] = static_cast<float>(mean);
+    gs[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float a = p.gamma[c] * gs[2 * g + 1];
+    float bb = p.beta[c] - gs[2 * g] * a;
+    if (p.film) {
+      const float fs = 1.0f + p.film[static_cast<size_t>(b) * p.film_ld + c];
+      const float fb = p.film[static_cast<size_t>(b) * p.film_ld + C + c];
+      a *= fs;
+      bb = bb * fs + fb;
+    }
+    sc[c] = a;
+    sh[c] = bb;
+  }
+  __syncthreads();
+
+  const int Ho = p.resample == 1 ? p.H * 2 : (p.resample == 2 ? p.H / 2 : p.H);
+  const int Wo = p.resample == 1 ? p.W * 2 : (p.resample == 2 ? p.W / 2 : p.W);
+  const int HWo = Ho * Wo;
+  const int vpp = C / 8;
+  const int p0 = blockIdx.x * ppc;
+  const int total = ppc * vpp;
+  for (int idx = tid; idx < total; idx += blockDim.x) {
+    const int px = p0 + idx / vpp;
+    if (px >= HWo) break;
+    const int c = (idx % vpp) * 8;
+    const float* src;
+    int Cx, cl;
+    if (c < p.C0) { src = p.src0; Cx = p.C0; cl = c; }
+    else          { src = p.src1; Cx = p.C1; cl = c - p.C0; }
+    const int ho = px / Wo, wo = px - ho * Wo;
+    float y[8], r[8];
+    float a8[8], b8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a8[j] = sc[c + j]; b8[j] = sh[c + j]; }
+    if (p.resample != 2) {
+      const int hi = p.resample == 1 ? ho >> 1 : ho, wi = p.resample == 1 ? wo >> 1 : wo;
+      const float4* s4 = reinterpret_cast<const float4*>(
+          src + (static_cast<size_t>(b) * HW + static_cast<size_t>(hi) * p.W + wi) * Cx + cl);
+      const float4 v0 = s4[0], v1 = s4[1];
+      r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = r[j] * a8[j] + b8[j];
+        y[j] = p.silu ? silu_f(t) : t;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { y[j] = 0.f; r[j] = 0.f; }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float4* s4 = reinterpret_cast<const float4*>(
+              src + (static_cast<size_t>(b) * HW + static_cast<size_t>(2 * ho + dy) * p.W + (2 * wo + dx)) * Cx + cl);
+          const float4 v0 = s4[0], v1 = s4[1];
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = v[j] * a8[j] + b8[j];
+            y[j] += p.silu ? silu_f(t) : t;
+            r[j] += v[j];
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { y[j] *= 0.25f; r[j] *= 0.25f; }
+    }
+    const size_t o = (static_cast<size_t>(b) * HWo + px) * C + c;
+    uint4 pk;
+    pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+    pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(p.out + o) = pk;
+    if (p.raw) {
+      uint4 pr;
+      pr.x = pack_bf16x2(r[0], r[1]); pr.y = pack_bf16x2(r[2], r[3]);
+      pr.z = pack_bf16x2(r[4], r[5]); pr.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(p.raw + o) = pr;
+    }
+    if (p.raw_f32) {
+      float4* d = reinterpret_cast<float4*>(p.raw_f32 + o);
+      d[0] = make_float4(r[0], r[1], r[2], r[3]);
+      d[1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
+int launch_gn_apply(const GnParams& p, int num_sms, cudaStream_t s) {
+  const int C = p.C0 + p.C1;
+  const int Ho = p.resample == 1 ? p.H * 2 : (p.resample == 2 ? p.H / 2 : p.H);
+  const int Wo = p.resample == 1 ? p.W * 2 : (p.resample == 2 ? p.W / 2 : p.W);
+  const int HWo = Ho * Wo;
+  int ppc = 256;
+  while (ppc > 16 && static_cast<long long>(p.B) * ((HWo + ppc - 1) / ppc) < 2LL * num_sms) ppc >>= 1;
+  dim3 grid((HWo + ppc - 1) / ppc, p.B);
+  const size_t smem = static_cast<size_t>(2 * C + 2 * p.groups) * sizeof(float);
+  gn_apply_kernel<<<grid, 256, smem, s>>>(p, ppc);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void stats_kernel(const float* __restrict__ src, float* __restrict__ stats, int HW, int C, int P) {
+  const int pp = blockIdx.x, b = blockIdx.y;
+  const int r0 = pp * 128;
+  const int r1 = min(HW, r0 + 128);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    const float* x = src + (static_cast<size_t>(b) * HW) * C + c;
+    for (int r = r0; r < r1; ++r) {
+      const float v = x[static_cast<size_t>(r) * C];
+      s += v;
+      q += v * v;
+    }
+    float* o = stats + ((static_cast<size_t>(b) * P + pp) * C + c) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+int launch_stats(const float* src, float* stats, int B, int HW, int C, cudaStream_t s) {
+  const int P = (HW + 127) / 128;
+  stats_kernel<<<dim3(P, B), 256, 0, s>>>(src, stats, HW, C, P);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void stats_reduce_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int C2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= C2) return;
+  float s = 0.f;
+  for (int pp = 0; pp < P; ++pp) s += in[(static_cast<size_t>(b) * P + pp) * C2 + i];
+  out[static_cast<size_t>(b) * C2 + i] = s;
+}
+
+int launch_stats_reduce(const float* in, float* out, int B, int P, int C, cudaStream_t s) {
+  const int C2 = 2 * C;
+  stats_reduce_kernel<<<dim3((C2 + 255) / 256, B), 256, 0, s>>>(in, out, P, C2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// input conv 3 -> Cout (fp32 SIMT: K = 27 is too thin for the tensor pipe)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_in_kernel(ConvInParams p) {
+  extern __shared__ float sw[];  // [27][Cout] + bias[Cout]
+  const int Cout = p.Cout;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = p.bias[i];
+  __syncthreads();
+  const int vpp = Cout / 4;
+  const int ppb = blockDim.x / vpp;
+  const int HW = p.H * p.W;
+  const long long gp = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / vpp;
+  if (gp >= static_cast<long long>(p.B) * HW) return;
+  const int co = (threadIdx.x % vpp) * 4;
+  const int b = static_cast<int>(gp / HW);
+  const int rem = static_cast<int>(gp - static_cast<long long>(b) * HW);
+  const int h = rem / p.W, w = rem - h * p.W;
+  float4 acc = *reinterpret_cast<const float4*>(sw + 27 * Cout + co);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int hh = h + ky - 1;
+    if (hh < 0 || hh >= p.H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ww = w + kx - 1;
+      if (ww < 0 || ww >= p.W) continue;
+      const float* xin = p.x + (static_cast<size_t>(b) * HW + static_cast<size_t>(hh) * p.W + ww) * 3;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float xv = xin[ci];
+        const float4 wv = *reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * Cout + co);
+        acc.x += xv * wv.x; acc.y += xv * wv.y; acc.z += xv * wv.z; acc.w += xv * wv.w;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(p.out + gp * Cout + co) = acc;
+}
+
+int launch_conv_in(const ConvInParams& p, cudaStream_t s) {
+  const int vpp = p.Cout / 4;
+  const int ppb = 256 / vpp;
+  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
+  const size_t smem = static_cast<size_t>(28 * p.Cout) * sizeof(float);
+  conv_in_kernel<<<static_cast<unsigned>((npix + ppb - 1) / ppb), 256, smem, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// output conv C -> 3|6 fused with the per-step update (warp per pixel, lanes across channels)
+// ------------------------------------------------------------------------------------------------
+constexpr int kConvOutPixPerWarp = 4;
+
+template <int CPL, int COUT>
+__global__ void __launch_bounds__(256) conv_out_kernel(ConvOutParams p) {
+  extern __shared__ float sw[];  // [9][CPL][COUT][32]
+  const int C = p.C;
+  for (int i = threadIdx.x; i < 9 * C * COUT; i += blockDim.x) {
+    const int o = i % COUT;
+    const int c = (i / COUT) % C;
+    const int tap = i / (COUT * C);
+    const int ln = c / CPL, j = c % CPL;
+    sw[((tap * CPL + j) * COUT + o) * 32 + ln] = p.w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int HW = p.H * p.W;
+  const long long npix = static_cast<long long>(p.B) * HW;
+  const long long base = (static_cast<long long>(blockIdx.x) * 8 + warp) * kConvOutPixPerWarp;
+  int step = 0;
+  float k[8];
+  CallParams cp;
+  cp.step_noise = nullptr; cp.seed = 0; cp.sample_offset = 0; cp.update_kind = 0;
+  if (p.mode == 1) {
+    step = *p.tables.step;
+    cp = *p.call;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i] = p.tables.coef[step * 8 + i];
+  }
+  for (int pi = 0; pi < kConvOutPixPerWarp; ++pi) {
+    const long long gp = base + pi;
+    if (gp >= npix) break;
+    const int b = static_cast<int>(gp / HW);
+    const int pix = static_cast<int>(gp - static_cast<long long>(b) * HW);
+    const int h = pix / p.W, w = pix - h * p.W;
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+      const __nv_bfloat16* src =
+          p.act + (static_cast<size_t>(b) * HW + static_cast<size_t>(hh) * p.W + ww) * C + lane * CPL;
+      float v[CPL];
+      if constexpr (CPL == 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+        unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
+      } else if constexpr (CPL == 4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(src);
+        unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+      } else {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(src);
+        unpack_bf16x2(u, v[0], v[1]);
+      }
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += v[j] * sw[((tap * CPL + j) * COUT + o) * 32 + lane];
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+      acc[o] += p.bias[o];
+    }
+    if (p.mode == 0) {
+      float val = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) val = (lane == o) ? acc[o] : val;
+      if (lane < COUT) p.out_nchw[(static_cast<size_t>(b) * COUT + lane) * HW + pix] = val;
+    } else if (lane < 3) {
+      float eps = 0.f, vv = 0.f;
+#pragma unroll
+      for (int o = 0; o < 3; ++o) eps = (lane == o) ? acc[o] : eps;
+      if constexpr (COUT >= 6) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) vv = (lane == o) ? acc[3 + o] : vv;
+      }
+      float* xp = p.x + gp * 3 + lane;
+      const float xv = *xp;
+      const float z = cp.step_noise
+                          ? cp.step_noise[((static_cast<size_t>(step) * p.B + b) * 3 + lane) * HW + pix]
+                          : dp_normal(cp.seed, cp.sample_offset + b, static_cast<unsigned>(step) + 1u,
+                                      static_cast<unsigned>(pix), lane);
+      float xn;
+      if (cp.update_kind == 0) {
+        xn = k[0] * xv + k[1] * eps + k[2] * z;
+      } else {
+        // guided_diffusion/gaussian_diffusion.py:277-284,305,317-322,438-446
+        float x0 = k[0] * xv - k[1] * eps;
+        x0 = fminf(1.f, fmaxf(-1.f, x0));
+        const float mean = k[2] * x0 + k[3] * xv;
+        const float frac = (vv + 1.f) * 0.5f;
+        const float logvar = frac * k[4] + (1.f - frac) * k[5];
+        xn = mean + k[6] * expf(0.5f * logvar) * z;
+      }
+      *xp = xn;
+    }
+  }
+}
+
+template <int CPL, int COUT>
+static int launch_conv_out_t(const ConvOutParams& p, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(9) * p.C * COUT * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel<CPL, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done = true;
+  }
+  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
+  const long long per_block = 8LL * kConvOutPixPerWarp;
+  conv_out_kernel<CPL, COUT><<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, smem, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
+  const int cpl = p.C / 32;
+  if (p.Cout == 3) {
+    if (cpl == 2) return launch_conv_out_t<2, 3>(p, s);
+    if (cpl == 4) return launch_conv_out_t<4, 3>(p, s);
+    if (cpl == 8) return launch_conv_out_t<8, 3>(p, s);
+  } else if (p.Cout == 6) {
+    if (cpl == 2) return launch_conv_out_t<2, 6>(p, s);
+    if (cpl == 4) return launch_conv_out_t<4, 6>(p, s);
+    if (cpl == 8) return launch_conv_out_t<8, 6>(p, s);
+  }
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+// ------------------------------------------------------------------------------------------------
+// short-sequence attention (T <= 64): one CTA per (head, sample), everything resident in smem
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_small_kernel(AttnSmallParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int T = p.T, d = p.d;
+  const int pitch = d + 2;  // bf16 elements; odd word pitch -> conflict-free row-strided reads
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smraw);
+  __nv_bfloat16* sk = sq + T * pitch;
+  __nv_bfloat16* sv = sk + T * pitch;
+  float* ss = reinterpret_cast<float*>(sv + T * pitch + ((T * pitch * 3) & 1));
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int ld = 3 * p.heads * d;
+  const __nv_bfloat16* g = p.qkv + static_cast<size_t>(b) * T * ld + head * d;
+  for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
+    const int r = i / d, c = i - r * d;
+    sq[r * pitch + c] = g[static_cast<size_t>(r) * ld + c];
+    sk[r * pitch + c] = g[static_cast<size_t>(r) * ld + p.heads * d + c];
+    sv[r * pitch + c] = g[static_cast<size_t>(r) * ld + 2 * p.heads * d + c];
+  }
+  __syncthreads();
+  for (int ij = threadIdx.x; ij < T * T; ij += blockDim.x) {
+    const int i = ij / T, j = ij - i * T;
+    float acc = 0.f;
+    for (int c = 0; c < d; c += 2) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(sq + i * pitch + c);
+      const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(sk + j * pitch + c);
+      acc += __bfloat162float(a.x) * __bfloat162float(bb.x) + __bfloat162float(a.y) * __bfloat162float(bb.y);
+    }
+    ss[i * (T + 1) + j] = acc * p.scale;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < T; i += 8) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, ss[i * (T + 1) + j]);
+    for (int m = 16; m > 0; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = __expf(ss[i * (T + 1) + j] - mx);
+      ss[i * (T + 1) + j] = e;
+      sum += e;
+    }
+    for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < T; j += 32) ss[i * (T + 1) + j] *= inv;
+  }
+  __syncthreads();
+  __nv_bfloat16* o = p.out + static_cast<size_t>(b) * T * (p.heads * d) + head * d;
+  for (int ic = threadIdx.x; ic < T * d; ic += blockDim.x) {
+    const int i = ic / d, c = ic - i * d;
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc += ss[i * (T + 1) + j] * __bfloat162float(sv[j * pitch + c]);
+    o[static_cast<size_t>(i) * (p.heads * d) + c] = __float2bfloat16_rn(acc);
+  }
+}
+
+int launch_attn_small(const AttnSmallParams& p, cudaStream_t s) {
+  const int pitch = p.d + 2;
+  const size_t smem = static_cast<size_t>(3) * p.T * pitch * 2 + 4 + static_cast<size_t>(p.T) * (p.T + 1) * 4;
+  if (smem > 227 * 1024) return static_cast<int>(cudaErrorInvalidValue);
+  cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  attn_small_kernel<<<dim3(p.heads, p.B), 256, smem, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// state init / layout conversion / step counter
+// ------------------------------------------------------------------------------------------------
+__global__ void init_state_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                  float* __restrict__ x, int B, int C, int HW, float sx, float se,
+                                  unsigned long long seed, unsigned long long sample_offset) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * C * HW;
+  if (i >= n) return;
+  const int pix = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+  const float e = noise ? noise[i] : dp_normal(seed, sample_offset + b, 0u, static_cast<unsigned>(pix), c);
+  x[(static_cast<size_t>(b) * HW + pix) * C + c] = sx * x0[i] + se * e;
+}
+
+int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nhwc, int B, int C, int HW,
+                      float sx, float se, unsigned long long seed, unsigned long long sample_offset,
+                      cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * C * HW;
+  init_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x0_nchw, noise_nchw, x_nhwc, B, C, HW,
+                                                                          sx, se, seed, sample_offset);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * C * HW;
+  if (i >= n) return;
+  const int pix = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+  out[i] = x[(static_cast<size_t>(b) * HW + pix) * C + c];
+}
+
+int launch_nhwc_to_nchw(const float* x_nhwc, float* out_nchw, int B, int C, int HW, cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * C * HW;
+  nhwc_to_nchw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x_nhwc, out_nchw, B, C, HW);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
+int launch_step_advance(int* step, cudaStream_t s) {
+  step_advance_kernel<<<1, 1, 0, s>>>(step);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace dp

@@ -1,0 +1,575 @@
+// dp_engine.cpp -- the C-ABI engine: device buffers, the lowered UNet program, CUDA-graph capture and the
+// device-resident purification loop (see include/diffpure_b200.h for the reference call sites it replaces).
+#include "diffpure_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dp_elem.cuh"
+#include "dp_gemm.cuh"
+#include "dp_tmap.h"
+
+namespace {
+
+std::string g_create_error;
+
+enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL };
+
+struct StatsReduce {
+  const float* in;
+  float* out;
+  int B, P, C;
+};
+
+struct Op {
+  OpKind kind;
+  dp::EmbedParams embed;
+  dp::GemmParams gemm;
+  int bn = 128;
+  bool softmax = false;
+  dp::GnParams gn;
+  dp_stats_desc stats;
+  StatsReduce sred;
+  dp::ConvInParams cin;
+  dp::ConvOutParams cout_;
+  dp::AttnSmallParams attn;
+};
+
+}  // namespace
+
+struct dp_engine {
+  int device = 0;
+  int num_sms = 148;
+  mutable std::string err;
+  std::vector<void*> buffers;
+  std::vector<size_t> sizes;
+  size_t total_bytes = 0;
+  std::vector<Op> ops;
+  bool finalized = false;
+  int B = 0, H = 0, W = 0, Cout = 0;
+  // engine-owned run state
+  float* x_state = nullptr;          // NHWC fp32 [B,H,W,3]
+  float* eps_out = nullptr;          // NCHW fp32 [B,Cout,H,W]
+  float* cond_per_sample = nullptr;  // [B]
+  int* d_step = nullptr;
+  float* d_cond = nullptr;
+  float* d_coef = nullptr;
+  int table_cap = 0;
+  dp::CallParams* d_call = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t g_forward = nullptr, g_step = nullptr;
+};
+
+namespace {
+
+int fail(const dp_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  return code;
+}
+int cuda_fail(const dp_engine* e, cudaError_t ce, const char* what) {
+  return fail(e, DP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+}
+#define DP_CUDA(e, call)                                  \
+  do {                                                    \
+    cudaError_t ce_ = (call);                             \
+    if (ce_ != cudaSuccess) return cuda_fail(e, ce_, #call); \
+  } while (0)
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2(long long v) {
+  int s = 0;
+  while ((1LL << s) < v) ++s;
+  return s;
+}
+
+dp::StepTables tables_of(dp_engine* e, int ncoef) {
+  dp::StepTables t;
+  t.step = e->d_step;
+  t.cond = e->d_cond;
+  t.coef = e->d_coef;
+  t.ncoef = ncoef;
+  return t;
+}
+
+int ensure_run_state(dp_engine* e) {
+  if (e->d_step) return DP_OK;
+  DP_CUDA(e, cudaSetDevice(e->device));
+  DP_CUDA(e, cudaMalloc(&e->d_step, 64));
+  DP_CUDA(e, cudaMemset(e->d_step, 0, 64));
+  e->table_cap = 4096;
+  DP_CUDA(e, cudaMalloc(&e->d_cond, sizeof(float) * e->table_cap));
+  DP_CUDA(e, cudaMalloc(&e->d_coef, sizeof(float) * e->table_cap * 8));
+  DP_CUDA(e, cudaMemset(e->d_cond, 0, sizeof(float) * e->table_cap));
+  DP_CUDA(e, cudaMemset(e->d_coef, 0, sizeof(float) * e->table_cap * 8));
+  DP_CUDA(e, cudaMalloc(&e->d_call, sizeof(dp::CallParams)));
+  DP_CUDA(e, cudaMemset(e->d_call, 0, sizeof(dp::CallParams)));
+  return DP_OK;
+}
+
+// mode: 0 = forward graph (per-sample cond, eps to eps_out), 1 = step graph (tables, fused update)
+int run_ops(dp_engine* e, int mode, cudaStream_t s) {
+  for (size_t i = 0; i < e->ops.size(); ++i) {
+    Op& op = e->ops[i];
+    int rc = 0;
+    switch (op.kind) {
+      case OP_EMBED: {
+        dp::EmbedParams p = op.embed;
+        p.cond_per_sample = mode == 0 ? e->cond_per_sample : nullptr;
+        rc = dp::launch_embed(p, s);
+        break;
+      }
+      case OP_GEMM:
+        rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s);
+        break;
+      case OP_GN:
+        rc = dp::launch_gn_apply(op.gn, e->num_sms, s);
+        break;
+      case OP_STATS:
+        rc = dp::launch_stats(op.stats.src, op.stats.stats, op.stats.B, op.stats.HW, op.stats.C, s);
+        break;
+      case OP_STATS_REDUCE:
+        rc = dp::launch_stats_reduce(op.sred.in, op.sred.out, op.sred.B, op.sred.P, op.sred.C, s);
+        break;
+      case OP_CONV_IN: {
+        dp::ConvInParams p = op.cin;
+        p.x = e->x_state;
+        rc = dp::launch_conv_in(p, s);
+        break;
+      }
+      case OP_CONV_OUT: {
+        dp::ConvOutParams p = op.cout_;
+        p.mode = mode;
+        p.out_nchw = e->eps_out;
+        p.x = e->x_state;
+        p.call = e->d_call;
+        rc = dp::launch_conv_out(p, s);
+        break;
+      }
+      case OP_ATTN_SMALL:
+        rc = dp::launch_attn_small(op.attn, s);
+        break;
+    }
+    if (rc != 0)
+      return fail(e, DP_ERR_CUDA,
+                  "launch of op " + std::to_string(i) + " (kind " + std::to_string(op.kind) +
+                      ") failed: " + cudaGetErrorString(static_cast<cudaError_t>(rc)));
+  }
+  if (mode == 1) {
+    int rc = dp::launch_step_advance(e->d_step, s);
+    if (rc) return fail(e, DP_ERR_CUDA, "launch_step_advance failed");
+  }
+  return DP_OK;
+}
+
+int capture(dp_engine* e, int mode, cudaGraphExec_t* out) {
+  cudaGraph_t graph = nullptr;
+  DP_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+  int rc = run_ops(e, mode, e->stream);
+  cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+  if (rc != DP_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess) return cuda_fail(e, ce, "cudaStreamEndCapture");
+  ce = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return cuda_fail(e, ce, "cudaGraphInstantiate");
+  return DP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_version(void) { return 100; }
+
+int dp_create(dp_engine** out, int device) {
+  if (!out) return DP_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(ce);
+    return DP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return DP_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, device);
+  if (ce != cudaSuccess) {
+    g_create_error = cudaGetErrorString(ce);
+    return DP_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "diffpure_b200 requires an sm_100a (B200) device, found sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor);
+    return DP_ERR_CUDA;
+  }
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    g_create_error = cudaGetErrorString(ce);
+    return DP_ERR_CUDA;
+  }
+  int rc = dp::gemm_init();
+  if (rc) {
+    g_create_error = std::string("gemm_init: ") + cudaGetErrorString(static_cast<cudaError_t>(rc));
+    return DP_ERR_CUDA;
+  }
+  dp_engine* e = new dp_engine();
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) {
+    g_create_error = cudaGetErrorString(ce);
+    delete e;
+    return DP_ERR_CUDA;
+  }
+  *out = e;
+  return DP_OK;
+}
+
+void dp_destroy(dp_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->g_forward) cudaGraphExecDestroy(e->g_forward);
+  if (e->g_step) cudaGraphExecDestroy(e->g_step);
+  for (void* p : e->buffers) cudaFree(p);
+  cudaFree(e->x_state);
+  cudaFree(e->eps_out);
+  cudaFree(e->cond_per_sample);
+  cudaFree(e->d_step);
+  cudaFree(e->d_cond);
+  cudaFree(e->d_coef);
+  cudaFree(e->d_call);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* dp_last_error(const dp_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+int dp_device_sm_count(const dp_engine* e) { return e ? e->num_sms : 0; }
+size_t dp_bytes_allocated(const dp_engine* e) { return e ? e->total_bytes : 0; }
+int dp_program_size(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
+int dp_launches_per_eval(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
+
+int dp_buffer_alloc(dp_engine* e, size_t bytes, int* buf_id) {
+  if (!e || !buf_id) return DP_ERR_INVALID;
+  DP_CUDA(e, cudaSetDevice(e->device));
+  void* p = nullptr;
+  const size_t padded = (bytes + 255) & ~static_cast<size_t>(255);
+  DP_CUDA(e, cudaMalloc(&p, padded ? padded : 256));
+  DP_CUDA(e, cudaMemset(p, 0, padded ? padded : 256));
+  e->buffers.push_back(p);
+  e->sizes.push_back(bytes);
+  e->total_bytes += padded;
+  *buf_id = static_cast<int>(e->buffers.size()) - 1;
+  return DP_OK;
+}
+
+void* dp_buffer_ptr(dp_engine* e, int buf_id) {
+  if (!e || buf_id < 0 || buf_id >= static_cast<int>(e->buffers.size())) return nullptr;
+  return e->buffers[buf_id];
+}
+
+int dp_buffer_write(dp_engine* e, int buf_id, size_t offset, const void* host_src, size_t bytes) {
+  if (!e || buf_id < 0 || buf_id >= static_cast<int>(e->buffers.size())) return DP_ERR_INVALID;
+  if (offset + bytes > e->sizes[buf_id]) return fail(e, DP_ERR_INVALID, "dp_buffer_write out of range");
+  DP_CUDA(e, cudaMemcpy(static_cast<char*>(e->buffers[buf_id]) + offset, host_src, bytes, cudaMemcpyHostToDevice));
+  return DP_OK;
+}
+
+int dp_buffer_read(dp_engine* e, int buf_id, size_t offset, void* host_dst, size_t bytes) {
+  if (!e || buf_id < 0 || buf_id >= static_cast<int>(e->buffers.size())) return DP_ERR_INVALID;
+  if (offset + bytes > e->sizes[buf_id]) return fail(e, DP_ERR_INVALID, "dp_buffer_read out of range");
+  DP_CUDA(e, cudaStreamSynchronize(e->stream));
+  DP_CUDA(e, cudaMemcpy(host_dst, static_cast<char*>(e->buffers[buf_id]) + offset, bytes, cudaMemcpyDeviceToHost));
+  return DP_OK;
+}
+
+int dp_op_embed(dp_engine* e, const dp_embed_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (int rc = ensure_run_state(e)) return rc;
+  if (d->dim % 2) return fail(e, DP_ERR_INVALID, "embed dim must be even");
+  Op op;
+  op.kind = OP_EMBED;
+  op.embed.out = static_cast<__nv_bfloat16*>(d->out_bf16);
+  op.embed.B = d->B;
+  op.embed.dim = d->dim;
+  op.embed.cos_first = d->cos_first;
+  op.embed.half_minus_1 = d->half_minus_1;
+  op.embed.cond_per_sample = nullptr;
+  op.embed.tables = tables_of(e, 3);
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->nseg < 1 || d->nseg > 2) return fail(e, DP_ERR_INVALID, "gemm: nseg must be 1 or 2");
+  if (d->N % 8 || d->N <= 0) return fail(e, DP_ERR_INVALID, "gemm: N must be a positive multiple of 8");
+  const int hw = d->H * d->W;
+  if (d->H > 1 && !(is_pow2(d->H) && is_pow2(d->W))) return fail(e, DP_ERR_INVALID, "gemm: H, W must be powers of two");
+  if (d->H > 1 && hw < 16) return fail(e, DP_ERR_INVALID, "gemm: H*W must be >= 16");
+  Op op;
+  op.kind = OP_GEMM;
+  dp::GemmParams& p = op.gemm;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = d->batch > 0 ? d->batch : 1;
+  op.softmax = d->softmax != 0;
+  // tile width
+  int bn = 128;
+  if (op.softmax) {
+    if (d->N != 128 && d->N != 256) return fail(e, DP_ERR_INVALID, "gemm softmax: N must be 128 or 256");
+    bn = d->N;
+  } else if (d->N % 256 == 0) {
+    dp::GemmParams probe;
+    std::memset(&probe, 0, sizeof(probe));
+    probe.batch = p.batch;
+    dp::gemm_fill_geometry(probe, d->B, d->H, d->W, d->N, 256);
+    if (static_cast<long long>(probe.m_tiles) * probe.n_tiles * probe.batch >= e->num_sms) bn = 256;
+  }
+  op.bn = bn;
+  dp::gemm_fill_geometry(p, d->B, d->H, d->W, d->N, bn);
+  const dp::TileBox tb = dp::gemm_tile_box(d->H, d->W);
+  std::string err;
+  long long ktotal = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const dp_gemm_aseg& a = d->a[s];
+    if (a.C % 64 || a.C <= 0) return fail(e, DP_ERR_INVALID, "gemm: segment channels must be a positive multiple of 64");
+    if (a.taps != 1 && a.taps != 9) return fail(e, DP_ERR_INVALID, "gemm: taps must be 1 or 9");
+    if (a.stride != 1 && a.stride != 2) return fail(e, DP_ERR_INVALID, "gemm: stride must be 1 or 2");
+    const int win = d->W * a.stride, hin = d->H * a.stride;
+    // plain / batched GEMM: the map spans all batch entries' rows
+    const int wdim = (d->H == 1) ? (p.batch > 1 ? (p.batch - 1) * d->a_batch_rows + d->W : d->W) : win;
+    if (dp::make_act_tmap(&p.a[s].tmap, a.act_bf16, a.C, a.c_total, wdim, hin, d->B, tb.bw, tb.bh, tb.bn, a.stride,
+                          &err))
+      return fail(e, DP_ERR_CUDA, "gemm: A tensor map: " + err);
+    p.a[s].taps = a.taps;
+    p.a[s].kchunks = a.C / 64;
+    p.a[s].stride = a.stride;
+    p.a[s].pad = a.pad;
+    ktotal += static_cast<long long>(a.taps) * a.C;
+  }
+  p.nseg = d->nseg;
+  if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, ktotal, d->w_rows, d->w_pitch, bn, &err))
+    return fail(e, DP_ERR_CUDA, "gemm: B tensor map: " + err);
+  p.a_batch_rows = d->a_batch_rows;
+  p.b_batch_rows = d->b_batch_rows;
+  p.out_batch_stride = d->out_batch_stride;
+  p.bias = d->bias;
+  p.bias_along_m = d->bias_along_m;
+  p.rowvec = d->rowvec;
+  p.rowvec_ld = d->rowvec_ld;
+  if (d->rowvec) {
+    if (!is_pow2(d->rowvec_rows_per_sample)) return fail(e, DP_ERR_INVALID, "gemm: rowvec rows/sample must be 2^k");
+    p.rowvec_shift = ilog2(d->rowvec_rows_per_sample);
+  }
+  p.rowscale = d->rowscale;
+  p.resid = d->resid;
+  p.alpha = d->alpha;
+  p.silu = d->silu;
+  p.out_f32 = d->out_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16);
+  p.ldc = d->ldc;
+  p.stats = d->stats;
+  p.softmax_scale = d->softmax_scale;
+  p.rowsum_out = d->rowsum_out;
+  if (op.softmax && (!p.out_bf16 || !p.rowsum_out)) return fail(e, DP_ERR_INVALID, "gemm softmax needs out_bf16 + rowsum_out");
+  if (!op.softmax && !p.out_f32 && !p.out_bf16) return fail(e, DP_ERR_INVALID, "gemm: no output");
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  const int C = d->C0 + d->C1;
+  if (d->C0 % 8 || d->C1 % 8 || C % d->groups) return fail(e, DP_ERR_INVALID, "gn: channel counts");
+  dp::GnParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.src0 = d->src0; p.stats0 = d->stats0; p.C0 = d->C0; p.P0 = d->P0;
+  p.src1 = d->src1; p.stats1 = d->stats1; p.C1 = d->C1; p.P1 = d->P1;
+  p.gamma = d->gamma; p.beta = d->beta; p.film = d->film; p.film_ld = d->film_ld;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.groups = d->groups; p.eps = d->eps; p.silu = d->silu;
+  p.resample = d->resample;
+  p.out = static_cast<__nv_bfloat16*>(d->out_bf16);
+  p.raw = static_cast<__nv_bfloat16*>(d->raw_bf16);
+  p.raw_f32 = d->raw_f32;
+  // Collapse long partial lists once (256x256 images: 512 partials / sample) so each CTA reads one row.
+  for (int which = 0; which < 2; ++which) {
+    const int P = which ? p.P1 : p.P0;
+    const int Cx = which ? p.C1 : p.C0;
+    const float* st = which ? p.stats1 : p.stats0;
+    if (Cx == 0 || P <= 16) continue;
+    int buf;
+    if (int rc = dp_buffer_alloc(e, static_cast<size_t>(d->B) * Cx * 2 * sizeof(float), &buf)) return rc;
+    Op r;
+    r.kind = OP_STATS_REDUCE;
+    r.sred.in = st;
+    r.sred.out = static_cast<float*>(e->buffers[buf]);
+    r.sred.B = d->B;
+    r.sred.P = P;
+    r.sred.C = Cx;
+    e->ops.push_back(r);
+    if (which) { p.stats1 = r.sred.out; p.P1 = 1; } else { p.stats0 = r.sred.out; p.P0 = 1; }
+  }
+  Op op;
+  op.kind = OP_GN;
+  op.gn = p;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_stats(dp_engine* e, const dp_stats_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  Op op;
+  op.kind = OP_STATS;
+  op.stats = *d;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_conv_in(dp_engine* e, const dp_conv_in_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->Cout % 4 || 256 % (d->Cout / 4)) return fail(e, DP_ERR_INVALID, "conv_in: Cout must divide 1024 and be a multiple of 4");
+  Op op;
+  op.kind = OP_CONV_IN;
+  op.cin.x = nullptr;
+  op.cin.w = d->w; op.cin.bias = d->bias; op.cin.out = d->out;
+  op.cin.B = d->B; op.cin.H = d->H; op.cin.W = d->W; op.cin.Cout = d->Cout;
+  e->ops.push_back(op);
+  if (d->stats) {
+    dp_stats_desc sd;
+    sd.src = d->out; sd.B = d->B; sd.HW = d->H * d->W; sd.C = d->Cout; sd.stats = d->stats;
+    return dp_op_stats(e, &sd);
+  }
+  return DP_OK;
+}
+
+int dp_op_conv_out(dp_engine* e, const dp_conv_out_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (int rc = ensure_run_state(e)) return rc;
+  if ((d->Cout != 3 && d->Cout != 6) || (d->C != 64 && d->C != 128 && d->C != 256))
+    return fail(e, DP_ERR_INVALID, "conv_out: Cout in {3,6}, C in {64,128,256}");
+  Op op;
+  op.kind = OP_CONV_OUT;
+  std::memset(&op.cout_, 0, sizeof(op.cout_));
+  op.cout_.act = static_cast<const __nv_bfloat16*>(d->act_bf16);
+  op.cout_.w = d->w; op.cout_.bias = d->bias;
+  op.cout_.B = d->B; op.cout_.H = d->H; op.cout_.W = d->W; op.cout_.C = d->C; op.cout_.Cout = d->Cout;
+  op.cout_.tables = tables_of(e, 8);
+  e->Cout = d->Cout;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->T > 64 || d->d % 2) return fail(e, DP_ERR_INVALID, "attn_small: T <= 64 and even head dim required");
+  Op op;
+  op.kind = OP_ATTN_SMALL;
+  op.attn.qkv = static_cast<const __nv_bfloat16*>(d->qkv_bf16);
+  op.attn.out = static_cast<__nv_bfloat16*>(d->out_bf16);
+  op.attn.B = d->B; op.attn.T = d->T; op.attn.heads = d->heads; op.attn.d = d->d; op.attn.scale = d->scale;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_finalize(dp_engine* e, int B, int H, int W) {
+  if (!e) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (e->ops.empty() || e->Cout == 0) return fail(e, DP_ERR_STATE, "program has no output conv");
+  if (int rc = ensure_run_state(e)) return rc;
+  e->B = B; e->H = H; e->W = W;
+  const size_t hw = static_cast<size_t>(H) * W;
+  DP_CUDA(e, cudaMalloc(&e->x_state, B * hw * 3 * sizeof(float)));
+  DP_CUDA(e, cudaMemset(e->x_state, 0, B * hw * 3 * sizeof(float)));
+  DP_CUDA(e, cudaMalloc(&e->eps_out, B * hw * e->Cout * sizeof(float)));
+  DP_CUDA(e, cudaMalloc(&e->cond_per_sample, sizeof(float) * B));
+  DP_CUDA(e, cudaMemset(e->cond_per_sample, 0, sizeof(float) * B));
+  // eager warm-up run of both modes (sets function attributes, surfaces launch errors), then capture
+  for (int mode = 0; mode < 2; ++mode) {
+    if (int rc = run_ops(e, mode, e->stream)) return rc;
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return cuda_fail(e, ce, "warm-up run of the program");
+  }
+  DP_CUDA(e, cudaMemset(e->d_step, 0, 64));
+  if (int rc = capture(e, 0, &e->g_forward)) return rc;
+  if (int rc = capture(e, 1, &e->g_step)) return rc;
+  e->finalized = true;
+  return DP_OK;
+}
+
+int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float* out_nchw, void* stream) {
+  if (!e || !x_nchw || !cond || !out_nchw) return DP_ERR_INVALID;
+  if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  DP_CUDA(e, cudaSetDevice(e->device));
+  DP_CUDA(e, cudaStreamSynchronize(user));  // inputs produced on the caller's stream are complete
+  const int HW = e->H * e->W;
+  int rc = dp::launch_init_state(x_nchw, x_nchw, e->x_state, e->B, 3, HW, 1.0f, 0.0f, 0, 0, e->stream);
+  if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
+  DP_CUDA(e, cudaMemcpyAsync(e->cond_per_sample, cond, sizeof(float) * e->B, cudaMemcpyDeviceToDevice, e->stream));
+  DP_CUDA(e, cudaGraphLaunch(e->g_forward, e->stream));
+  DP_CUDA(e, cudaMemcpyAsync(out_nchw, e->eps_out, sizeof(float) * e->B * e->Cout * HW, cudaMemcpyDeviceToDevice,
+                             e->stream));
+  DP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return DP_OK;
+}
+
+int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_purify_params* p, void* stream) {
+  if (!e || !x0_nchw || !out_nchw || !p) return DP_ERR_INVALID;
+  if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
+  if (p->steps <= 0 || p->steps > e->table_cap) return fail(e, DP_ERR_INVALID, "steps out of range");
+  if (p->ncoef < 3 || p->ncoef > 8) return fail(e, DP_ERR_INVALID, "ncoef out of range");
+  const int want = p->update_kind == DP_UPDATE_LEARNED_RANGE ? 6 : 3;
+  if (e->Cout != want && !(p->update_kind == DP_UPDATE_LINEAR && e->Cout == 6))
+    return fail(e, DP_ERR_INVALID, "update_kind does not match the model's output channels");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  DP_CUDA(e, cudaSetDevice(e->device));
+  DP_CUDA(e, cudaStreamSynchronize(user));
+  cudaStream_t s = e->stream;
+  // per-step tables: the captured graph reads cond[*step] / coef[*step][:]
+  std::vector<float> coef8(static_cast<size_t>(p->steps) * 8, 0.f);
+  for (int i = 0; i < p->steps; ++i)
+    for (int j = 0; j < p->ncoef; ++j) coef8[static_cast<size_t>(i) * 8 + j] = p->coef[static_cast<size_t>(i) * p->ncoef + j];
+  // tables are laid out with a fixed pitch of 8 so the graph's kernel parameters never change
+  DP_CUDA(e, cudaMemcpyAsync(e->d_cond, p->cond, sizeof(float) * p->steps, cudaMemcpyHostToDevice, s));
+  DP_CUDA(e, cudaMemcpyAsync(e->d_coef, coef8.data(), sizeof(float) * coef8.size(), cudaMemcpyHostToDevice, s));
+  dp::CallParams cp;
+  cp.step_noise = p->step_noise;
+  cp.seed = p->seed;
+  cp.sample_offset = p->sample_offset;
+  cp.update_kind = p->update_kind;
+  DP_CUDA(e, cudaMemcpyAsync(e->d_call, &cp, sizeof(cp), cudaMemcpyHostToDevice, s));
+  DP_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int), s));
+  DP_CUDA(e, cudaStreamSynchronize(s));  // host staging buffers (coef8, cp) may go out of scope
+  // the conv_out node was captured with update_kind / ncoef of the program; patch through the tables
+  const int HW = e->H * e->W;
+  int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
+                                 p->seed, p->sample_offset, s);
+  if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
+  for (int i = 0; i < p->steps; ++i) DP_CUDA(e, cudaGraphLaunch(e->g_step, s));
+  rc = dp::launch_nhwc_to_nchw(e->x_state, out_nchw, e->B, 3, HW, s);
+  if (rc) return fail(e, DP_ERR_CUDA, "nhwc_to_nchw launch failed");
+  DP_CUDA(e, cudaStreamSynchronize(s));
+  return DP_OK;
+}
+
+float dp_normal_host(uint64_t seed, uint64_t sample, uint32_t stream, uint32_t pixel, int c) {
+  return dp::dp_normal(seed, sample, stream, pixel, c);
+}
+
+}  // extern "C"

@@ -362,7 +362,7 @@ int gemm_init() {
 
 TileBox gemm_tile_box(int H, int W) {
   TileBox t;
-  if (W >= kBlockM) {
+  if (W >= kBlockM || H == 1) {  // plain GEMM rows (H == 1): always 128-row boxes, OOB rows read as zero
     t.bw = kBlockM;
     t.bh = 1;
     t.bn = 1;
@@ -381,7 +381,7 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn) {
   p.bw = t.bw;
   p.bh = t.bh;
   const int hw = H * W;
-  if (hw >= kBlockM) {
+  if (hw >= kBlockM || H == 1) {
     p.imgs_per_tile = 1;
     p.tiles_w = (W + t.bw - 1) / t.bw;
     const int tiles_h = (H + t.bh - 1) / t.bh;

@@ -65,8 +65,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > DP_MBAR_TIMEOUT_CYCLES) {
-      printf("dp: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
+      if ((threadIdx.x & 31) == 0)
+        printf("dp: mbarrier timeout block %d warp %d bar 0x%x parity %u\n", (int)blockIdx.x,
+               (int)(threadIdx.x >> 5), bar, parity);
       __trap();
     }
   }

@@ -1,0 +1,233 @@
+"""Engine backend: materialises a `Program` through the C ABI and runs it.
+
+PyTorch is used only for device memory of the caller-visible tensors and for streams; every kernel on the
+path lives in libdiffpure_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .program import Program, View
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+def _to_bytes(t, dtype):
+    t = t.detach().cpu().contiguous()
+    if dtype == "bf16":
+        return t.to(torch.bfloat16).view(torch.int16).numpy().tobytes()
+    return t.to(torch.float32).numpy().tobytes()
+
+
+class Engine:
+    def __init__(self, program: Program, device=0, pool=True):
+        self.lib = _lib.load()
+        self.program = program
+        self.device = int(device)
+        self.B, self.H, self.W = program.B, program.H, program.W
+        self.out_channels = program.meta.get("out_channels", 3)
+        h = C.c_void_p()
+        rc = self.lib.dp_create(C.byref(h), self.device)
+        if rc != 0:
+            raise _lib.DPError(f"dp_create failed (code {rc}): {self.lib.dp_last_error(None).decode()}")
+        self.h = h
+        self._ptr = {}       # tensor index -> device address
+        self._loc = {}       # tensor index -> (buffer id, byte offset)
+        self.const_bytes = 0
+        self.act_bytes = 0
+        try:
+            self._upload_constants()
+            self._place_activations(pool)
+            self._emit_ops()
+            self._check(self.lib.dp_finalize(self.h, self.B, self.H, self.W), "dp_finalize")
+        except Exception:
+            self.close()
+            raise
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        _lib.check(self.lib, self.h, rc, what)
+
+    def _alloc(self, nbytes):
+        bid = C.c_int()
+        self._check(self.lib.dp_buffer_alloc(self.h, nbytes, C.byref(bid)), "dp_buffer_alloc")
+        return bid.value, self.lib.dp_buffer_ptr(self.h, bid.value)
+
+    def _upload_constants(self):
+        """All weights / tables go into one blob (one allocation, one upload; one NCCL broadcast when sharded)."""
+        consts = [t for t in self.program.tensors if t.init is not None]
+        offs, total = {}, 0
+        for t in consts:
+            offs[t.index] = total
+            total += _align(t.nbytes)
+        blob = bytearray(total)
+        for t in consts:
+            b = _to_bytes(t.init, t.dtype)
+            assert len(b) == t.nbytes, (t.name, len(b), t.nbytes)
+            blob[offs[t.index]:offs[t.index] + len(b)] = b
+        self.const_bytes = total
+        if total == 0:
+            return
+        bid, base = self._alloc(total)
+        buf = (C.c_char * total).from_buffer(blob)
+        self._check(self.lib.dp_buffer_write(self.h, bid, 0, C.addressof(buf), total), "dp_buffer_write")
+        self.weights_buffer = (bid, base, total)
+        for t in consts:
+            self._ptr[t.index] = base + offs[t.index]
+            self._loc[t.index] = (bid, offs[t.index])
+
+    def _place_activations(self, pool):
+        prog = self.program
+        first, last = prog.first_use(), prog.last_use()
+        acts = [t for t in prog.tensors if t.init is None and t.index in first]
+        by_first = {}
+        for t in acts:
+            by_first.setdefault(first[t.index], []).append(t)
+        by_last = {}
+        for t in acts:
+            by_last.setdefault(last[t.index], []).append(t)
+        free = []      # (nbytes, ptr)
+        owner = {}     # tensor index -> (nbytes, ptr)
+        for i in range(len(prog.ops)):
+            for t in by_first.get(i, []):
+                need = _align(t.nbytes)
+                pick = None
+                if pool:
+                    cands = [f for f in free if need <= f[0] <= 2 * need]
+                    if cands:
+                        pick = min(cands)
+                        free.remove(pick)
+                if pick is None:
+                    bid, ptr = self._alloc(need)
+                    pick = (need, ptr, bid)
+                    self.act_bytes += need
+                owner[t.index] = pick
+                self._ptr[t.index] = pick[1]
+                self._loc[t.index] = (pick[2], 0)
+            for t in by_last.get(i, []):
+                free.append(owner[t.index])
+
+    def _p(self, v, elem_bytes=None):
+        if v is None:
+            return None
+        assert isinstance(v, View)
+        eb = 4 if v.tensor.dtype == "f32" else 2
+        return self._ptr[v.tensor.index] + v.offset * eb
+
+    def _emit_ops(self):
+        L = self.lib
+        for op in self.program.ops:
+            a = op.args
+            if op.kind == "embed":
+                d = _lib.EmbedDesc(self._p(a["out"]), a["B"], a["dim"], a["cos_first"], a["half_minus_1"])
+                self._check(L.dp_op_embed(self.h, C.byref(d)), "dp_op_embed")
+            elif op.kind == "gemm":
+                d = _lib.GemmDesc()
+                for i, seg in enumerate(a["a"]):
+                    d.a[i] = _lib.GemmASeg(self._p(seg.act), seg.C, seg.c_total, seg.taps, seg.stride, seg.pad)
+                d.nseg = len(a["a"])
+                d.w_bf16 = self._p(a["w"]); d.w_rows = a["w_rows"]; d.w_pitch = a["w_pitch"]
+                d.B, d.H, d.W, d.N = a["B"], a["H"], a["W"], a["N"]
+                d.batch, d.a_batch_rows, d.b_batch_rows = a["batch"], a["a_batch_rows"], a["b_batch_rows"]
+                d.out_batch_stride = a["out_batch_stride"]
+                d.bias = self._p(a["bias"]); d.bias_along_m = a["bias_along_m"]
+                d.rowvec = self._p(a["rowvec"]); d.rowvec_ld = a["rowvec_ld"]
+                d.rowvec_rows_per_sample = a["rowvec_rows_per_sample"]
+                d.rowscale = self._p(a["rowscale"]); d.resid = self._p(a["resid"])
+                d.alpha = a["alpha"]; d.silu = a["silu"]
+                d.out_f32 = self._p(a["out_f32"]); d.out_bf16 = self._p(a["out_bf16"]); d.ldc = a["ldc"]
+                d.stats = self._p(a["stats"])
+                d.softmax = a["softmax"]; d.softmax_scale = a["softmax_scale"]; d.rowsum_out = self._p(a["rowsum_out"])
+                self._check(L.dp_op_gemm(self.h, C.byref(d)), "dp_op_gemm")
+            elif op.kind == "gn_apply":
+                d = _lib.GnDesc(self._p(a["src0"]), self._p(a["stats0"]), a["C0"], a["P0"], self._p(a["src1"]),
+                                self._p(a["stats1"]), a["C1"], a["P1"], self._p(a["gamma"]), self._p(a["beta"]),
+                                self._p(a["film"]), a["film_ld"], a["B"], a["H"], a["W"], a["groups"], a["eps"],
+                                a["silu"], a["resample"], self._p(a["out_bf16"]), self._p(a["raw_bf16"]),
+                                self._p(a["raw_f32"]))
+                self._check(L.dp_op_gn_apply(self.h, C.byref(d)), "dp_op_gn_apply")
+            elif op.kind == "conv_in":
+                d = _lib.ConvInDesc(self._p(a["w"]), self._p(a["bias"]), self._p(a["out"]), self._p(a["stats"]),
+                                    a["B"], a["H"], a["W"], a["Cout"])
+                self._check(L.dp_op_conv_in(self.h, C.byref(d)), "dp_op_conv_in")
+            elif op.kind == "conv_out":
+                d = _lib.ConvOutDesc(self._p(a["act"]), self._p(a["w"]), self._p(a["bias"]), a["B"], a["H"], a["W"],
+                                     a["C"], a["Cout"])
+                self._check(L.dp_op_conv_out(self.h, C.byref(d)), "dp_op_conv_out")
+            elif op.kind == "attn_small":
+                d = _lib.AttnSmallDesc(self._p(a["qkv"]), self._p(a["out"]), a["B"], a["T"], a["heads"], a["d"],
+                                       a["scale"])
+                self._check(L.dp_op_attn_small(self.h, C.byref(d)), "dp_op_attn_small")
+            else:
+                raise ValueError(f"unknown op kind {op.kind}")
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def launches_per_eval(self):
+        return self.lib.dp_launches_per_eval(self.h)
+
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    def _prep(self, x):
+        assert x.shape == (self.B, 3, self.H, self.W), (tuple(x.shape), (self.B, 3, self.H, self.W))
+        return x.to(device=self._dev(), dtype=torch.float32).contiguous()
+
+    def unet_forward(self, x, cond):
+        """x: [B,3,H,W]; cond: [B] float. Returns the UNet output [B,Cout,H,W] (fp32, on the engine's device)."""
+        x = self._prep(x)
+        cond = cond.to(device=self._dev(), dtype=torch.float32).contiguous()
+        assert cond.shape == (self.B,)
+        out = torch.empty((self.B, self.out_channels, self.H, self.W), device=self._dev(), dtype=torch.float32)
+        torch.cuda.current_stream(self._dev()).synchronize()
+        self._check(self.lib.dp_unet_forward(self.h, x.data_ptr(), cond.data_ptr(), out.data_ptr(), None),
+                    "dp_unet_forward")
+        return out
+
+    def purify(self, x0, cond, coef, init_scale_x, init_scale_e, *, update_kind=_lib.DP_UPDATE_LINEAR,
+               init_noise=None, step_noise=None, seed=0, sample_offset=0):
+        """Runs the whole loop on the device. cond: [steps] host floats; coef: [steps, ncoef] host floats."""
+        x0 = self._prep(x0)
+        cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float32))
+        coef = np.ascontiguousarray(np.asarray(coef, dtype=np.float32))
+        steps = cond.shape[0]
+        assert coef.ndim == 2 and coef.shape[0] == steps
+        if init_noise is not None:
+            init_noise = init_noise.to(device=self._dev(), dtype=torch.float32).contiguous()
+            assert init_noise.shape == x0.shape
+        if step_noise is not None:
+            step_noise = step_noise.to(device=self._dev(), dtype=torch.float32).contiguous()
+            assert step_noise.shape == (steps,) + tuple(x0.shape)
+        out = torch.empty_like(x0)
+        p = _lib.PurifyParams(steps, update_kind, coef.shape[1], cond.ctypes.data, coef.ctypes.data,
+                              float(init_scale_x), float(init_scale_e),
+                              init_noise.data_ptr() if init_noise is not None else None,
+                              step_noise.data_ptr() if step_noise is not None else None, int(seed),
+                              int(sample_offset))
+        torch.cuda.current_stream(self._dev()).synchronize()
+        self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), None), "dp_purify")
+        return out
+
+    def read_tensor(self, name):
+        """Debug: copy an engine tensor back to the host (intermediate values need pool=False)."""
+        t = next(t for t in self.program.tensors if t.name == name)
+        bid, off = self._loc[t.index]
+        host = np.empty(t.numel, dtype=np.int16 if t.dtype == "bf16" else np.float32)
+        self._check(self.lib.dp_buffer_read(self.h, bid, off, host.ctypes.data, host.nbytes), "dp_buffer_read")
+        out = torch.from_numpy(host)
+        return out.view(torch.bfloat16).float() if t.dtype == "bf16" else out
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.dp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,246 @@
+"""Lowering of the DDPM++ / NCSN++ score network to the engine program.
+
+Mirrors score_sde/models/ncsnpp.py:35-381 for DiffPure's CIFAR-10 configuration (configs/cifar10.yml:18-40):
+biggan res-blocks (layerspp.py:212-274), AttnBlockpp (layerspp.py:62-91), NIN (layers.py:546-555),
+positional timestep embedding (layers.py:515-529), naive 2x up / 2x2-mean down (up_or_down_sampling.py:67-77).
+The state_dict uses the reference's parameter names (`all_modules.<i>.<...>`).
+
+Fusions per res-block (reference: 2 GroupNorm + 2 SiLU + 2-3 conv + Linear + adds + optional resample/cat
+= ~14 ATen ops) -> 4 kernels:
+  gn_apply(GN0+SiLU [+up/down] [+concat] [+bf16 copy of x for the 1x1 shortcut])
+  gemm(Conv_0 3x3 + bias + Dense_0(SiLU(temb)) add + GN1 partial statistics)
+  gn_apply(GN1+SiLU)
+  gemm(Conv_1 3x3 [+ Conv_2 1x1 as extra K] + biases + residual + 1/sqrt(2) + next block's GN statistics)
+All per-block Dense_0(SiLU(temb)) projections are one GEMM per step.
+"""
+from types import SimpleNamespace
+
+import torch
+
+from .lowering_common import INV_SQRT2, Act, act_seg, new_act, pack_conv1x1, pack_conv3x3, pack_conv_in, \
+    pack_conv_out, pad_rows
+from .program import Program, view
+
+
+def cifar10_cfg():
+    return SimpleNamespace(image_size=32, num_channels=3, nf=128, ch_mult=(1, 2, 2, 2), num_res_blocks=8,
+                           attn_resolutions=(16,))
+
+
+def cfg_from_reference(config):
+    """Accepts the reference's yaml namespace (config.model.*, config.data.*)."""
+    m, d = config.model, config.data
+    assert m.name == "ncsnpp" and m.resblock_type.lower() == "biggan" and not m.fir and m.skip_rescale \
+        and m.progressive == "none" and m.progressive_input == "none" and m.embedding_type == "positional" \
+        and m.conditional and m.nonlinearity.lower() == "swish", "unsupported NCSN++ variant"
+    return SimpleNamespace(image_size=d.image_size, num_channels=d.num_channels, nf=m.nf, ch_mult=tuple(m.ch_mult),
+                           num_res_blocks=m.num_res_blocks, attn_resolutions=tuple(m.attn_resolutions))
+
+
+def _groups(c):
+    return min(c // 4, 32)
+
+
+def module_plan(cfg):
+    """(kind, kwargs) per `all_modules` index, in the reference's construction order (ncsnpp.py:68-230)."""
+    nf, ch_mult, nrb = cfg.nf, cfg.ch_mult, cfg.num_res_blocks
+    nres = len(ch_mult)
+    res_at = [cfg.image_size // (2 ** i) for i in range(nres)]
+    plan = [("lin0", {}), ("lin1", {}), ("conv_in", {})]
+    skips = [nf]
+    c = nf
+    for lvl in range(nres):
+        for _ in range(nrb):
+            co = nf * ch_mult[lvl]
+            plan.append(("res", dict(cin=c, cout=co, mode=0, role="down")))
+            c = co
+            if res_at[lvl] in cfg.attn_resolutions:
+                plan.append(("attn", dict(c=c)))
+            skips.append(c)
+        if lvl != nres - 1:
+            plan.append(("res", dict(cin=c, cout=c, mode=2, role="downsample")))
+            skips.append(c)
+    plan += [("res", dict(cin=c, cout=c, mode=0, role="mid")), ("attn", dict(c=c)),
+             ("res", dict(cin=c, cout=c, mode=0, role="mid"))]
+    for lvl in reversed(range(nres)):
+        for _ in range(nrb + 1):
+            co = nf * ch_mult[lvl]
+            plan.append(("res", dict(cin=c + skips.pop(), cout=co, mode=0, role="up")))
+            c = co
+        if res_at[lvl] in cfg.attn_resolutions:
+            plan.append(("attn", dict(c=c)))
+        if lvl != 0:
+            plan.append(("res", dict(cin=c, cout=c, mode=1, role="upsample")))
+    assert not skips
+    plan += [("gn_out", dict(c=c)), ("conv_out", dict(c=c))]
+    return plan
+
+
+def lower(cfg, sd, B):
+    """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU)."""
+    S = cfg.image_size
+    prog = Program(B, S, S)
+    plan = module_plan(cfg)
+    nf = cfg.nf
+    temb_dim = 4 * nf
+
+    def P(i, name):
+        return sd[f"all_modules.{i}.{name}"].detach().float().cpu()
+
+    # ---- time embedding MLP + all per-block Dense_0 projections in one GEMM -------------------------
+    dense_off = {}
+    dense_w, dense_b = [], []
+    off = 0
+    for i, (kind, kw) in enumerate(plan):
+        if kind == "res":
+            dense_off[i] = off
+            dense_w.append(P(i, "Dense_0.weight"))
+            dense_b.append(P(i, "Dense_0.bias"))
+            off += kw["cout"]
+    n_all = (off + 127) // 128 * 128
+    w_all = pad_rows(torch.cat(dense_w, 0))
+    b_all = torch.cat(dense_b + [torch.zeros(n_all - off)], 0)
+
+    emb = prog.tensor("temb.emb", B * nf, "bf16")
+    prog.embed(emb, B, nf, cos_first=0, half_minus_1=1)                      # layers.py:515-529
+    t1 = prog.tensor("temb.h1", B * temb_dim, "bf16")
+    prog.gemm([act_seg(emb, nf)], prog.const_bf16("temb.w0", P(0, "weight")), temb_dim, nf, 1, 1, B, temb_dim,
+              bias=prog.const_f32("temb.b0", P(0, "bias")), silu=1, out_bf16=t1)   # ncsnpp.py:252-254
+    t2 = prog.tensor("temb.h2", B * temb_dim, "bf16")
+    prog.gemm([act_seg(t1, temb_dim)], prog.const_bf16("temb.w1", P(1, "weight")), temb_dim, temb_dim, 1, 1, B,
+              temb_dim, bias=prog.const_f32("temb.b1", P(1, "bias")), silu=1, out_bf16=t2)  # SiLU: every consumer
+    temb_all = prog.tensor("temb.all", B * n_all, "f32")                      # applies act(temb), layerspp.py:263
+    prog.gemm([act_seg(t2, temb_dim)], prog.const_bf16("temb.wall", w_all), n_all, temb_dim, 1, 1, B, n_all,
+              bias=prog.const_f32("temb.ball", b_all), out_f32=temb_all)
+
+    # ---- blocks ---------------------------------------------------------------------------------------
+    def resblock(i, kw, x0: Act, x1: Act = None):
+        """ResnetBlockBigGANpp.forward, layerspp.py:242-274."""
+        cin, cout, mode = kw["cin"], kw["cout"], kw["mode"]
+        assert cin == x0.C + (x1.C if x1 else 0)
+        H, W = x0.H, x0.W
+        Ho, Wo = (H * 2, W * 2) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
+        shortcut = (cin != cout) or mode != 0
+        name = f"m{i}"
+        a0 = prog.tensor(name + ".a0", B * Ho * Wo * cin, "bf16")
+        xb = prog.tensor(name + ".xb", B * Ho * Wo * cin, "bf16") if shortcut else None
+        prog.gn_apply(src0=x0.t, stats0=x0.stats, C0=x0.C, P0=x0.P,
+                      src1=x1.t if x1 else None, stats1=x1.stats if x1 else None, C1=x1.C if x1 else 0,
+                      P1=x1.P if x1 else 0,
+                      gamma=prog.const_f32(name + ".gn0.w", P(i, "GroupNorm_0.weight")),
+                      beta=prog.const_f32(name + ".gn0.b", P(i, "GroupNorm_0.bias")),
+                      B=B, H=H, W=W, groups=_groups(cin), eps=1e-6, silu=1, resample=mode, out_bf16=a0, raw_bf16=xb)
+        h = new_act(prog, name + ".h", B, cout, Ho, Wo)
+        prog.gemm([act_seg(a0, cin, taps=9)], prog.const_bf16(name + ".w0", pack_conv3x3(P(i, "Conv_0.weight"))),
+                  cout, 9 * cin, B, Ho, Wo, cout, bias=prog.const_f32(name + ".b0", P(i, "Conv_0.bias")),
+                  rowvec=view(temb_all, dense_off[i]), rowvec_ld=n_all, rowvec_rows_per_sample=Ho * Wo,
+                  out_f32=h.t, stats=h.stats)
+        a1 = prog.tensor(name + ".a1", B * Ho * Wo * cout, "bf16")
+        prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P,
+                      gamma=prog.const_f32(name + ".gn1.w", P(i, "GroupNorm_1.weight")),
+                      beta=prog.const_f32(name + ".gn1.b", P(i, "GroupNorm_1.bias")),
+                      B=B, H=Ho, W=Wo, groups=_groups(cout), eps=1e-6, silu=1, out_bf16=a1)
+        out = new_act(prog, name + ".out", B, cout, Ho, Wo)
+        w1 = pack_conv3x3(P(i, "Conv_1.weight"))
+        if shortcut:
+            w = torch.cat([w1, pack_conv1x1(P(i, "Conv_2.weight"))], dim=1)
+            bias = P(i, "Conv_1.bias") + P(i, "Conv_2.bias")
+            prog.gemm([act_seg(a1, cout, taps=9), act_seg(xb, cin)], prog.const_bf16(name + ".w1", w), cout,
+                      9 * cout + cin, B, Ho, Wo, cout, bias=prog.const_f32(name + ".b1", bias), alpha=INV_SQRT2,
+                      out_f32=out.t, stats=out.stats)
+        else:
+            prog.gemm([act_seg(a1, cout, taps=9)], prog.const_bf16(name + ".w1", w1), cout, 9 * cout, B, Ho, Wo, cout,
+                      bias=prog.const_f32(name + ".b1", P(i, "Conv_1.bias")), resid=x0.t, alpha=INV_SQRT2,
+                      out_f32=out.t, stats=out.stats)
+        return out
+
+    def attnblock(i, kw, x: Act):
+        """AttnBlockpp.forward, layerspp.py:75-91 (single head of width C, scale C^-1/2, skip_rescale)."""
+        C, H, W = x.C, x.H, x.W
+        T = H * W
+        name = f"m{i}"
+        hn = prog.tensor(name + ".hn", B * T * C, "bf16")
+        prog.gn_apply(src0=x.t, stats0=x.stats, C0=C, P0=x.P,
+                      gamma=prog.const_f32(name + ".gn.w", P(i, "GroupNorm_0.weight")),
+                      beta=prog.const_f32(name + ".gn.b", P(i, "GroupNorm_0.bias")),
+                      B=B, H=H, W=W, groups=_groups(C), eps=1e-6, silu=0, out_bf16=hn)
+        wq, wk, wv = (P(i, f"NIN_{j}.W").t().contiguous() for j in range(3))   # NIN: y = x.W + b, W is [in, out]
+        bq, bk, bv = (P(i, f"NIN_{j}.b") for j in range(3))
+        o = prog.tensor(name + ".o", B * T * C, "bf16")
+        if T <= 64:
+            qkv = prog.tensor(name + ".qkv", B * T * 3 * C, "bf16")
+            prog.gemm([act_seg(hn, C)], prog.const_bf16(name + ".wqkv", torch.cat([wq, wk, wv], 0)),
+                      3 * C, C, 1, 1, B * T, 3 * C, bias=prog.const_f32(name + ".bqkv", torch.cat([bq, bk, bv])),
+                      out_bf16=qkv)
+            prog.attn_small(qkv, o, B, T, 1, C, C ** -0.5)
+        else:
+            assert T in (128, 256), "tensor-core attention path needs T in {128, 256}"
+            qk = prog.tensor(name + ".qk", B * T * 2 * C, "bf16")
+            prog.gemm([act_seg(hn, C)], prog.const_bf16(name + ".wqk", torch.cat([wq, wk], 0)), 2 * C, C, 1, 1,
+                      B * T, 2 * C, bias=prog.const_f32(name + ".bqk", torch.cat([bq, bk])), out_bf16=qk)
+            # V^T per sample: [C, T] = Wv[C, C] . hn_b[T, C]^T   (weights as the A operand, bias along M)
+            vt = prog.tensor(name + ".vt", B * C * T, "bf16")
+            prog.gemm([act_seg(prog.const_bf16(name + ".wv", wv), C)], hn, B * T, C, 1, 1, C, T, batch=B,
+                      a_batch_rows=0, b_batch_rows=T, out_batch_stride=C * T,
+                      bias=prog.const_f32(name + ".bv", bv), bias_along_m=1, out_bf16=vt, ldc=T)
+            # P = exp(scale * (q.k^T - rowmax)) (bf16) and its row sums
+            pm = prog.tensor(name + ".p", B * T * T, "bf16")
+            rs = prog.tensor(name + ".rowsum", B * T, "f32")
+            prog.gemm([act_seg(qk, C, c_total=2 * C)], view(qk, C), B * T, 2 * C, 1, 1, T, T, batch=B,
+                      a_batch_rows=T, b_batch_rows=T, out_batch_stride=T * T, out_bf16=pm, ldc=T, softmax=1,
+                      softmax_scale=C ** -0.5, rowsum_out=rs)
+            prog.gemm([act_seg(pm, T)], vt, B * C, T, 1, 1, T, C, batch=B, a_batch_rows=T, b_batch_rows=C,
+                      out_batch_stride=T * C, rowscale=rs, out_bf16=o, ldc=C)
+        out = new_act(prog, name + ".out", B, C, H, W)
+        prog.gemm([act_seg(o, C)], prog.const_bf16(name + ".w3", P(i, "NIN_3.W").t().contiguous()), C, C, B, H, W, C,
+                  bias=prog.const_f32(name + ".b3", P(i, "NIN_3.b")), resid=x.t, alpha=INV_SQRT2, out_f32=out.t,
+                  stats=out.stats)
+        return out
+
+    # ---- walk the module list exactly as NCSNpp.forward does (ncsnpp.py:263-381) ----------------------
+    idx = 2
+    h0 = new_act(prog, "conv_in.out", B, nf, S, S)
+    prog.conv_in(prog.const_f32("conv_in.w", pack_conv_in(P(2, "weight"))), prog.const_f32("conv_in.b", P(2, "bias")),
+                 h0.t, h0.stats, B, S, S, nf)
+    idx = 3
+    hs = [h0]
+    nres = len(cfg.ch_mult)
+    for lvl in range(nres):
+        for _ in range(cfg.num_res_blocks):
+            kind, kw = plan[idx]
+            h = resblock(idx, kw, hs[-1])
+            idx += 1
+            if h.H in cfg.attn_resolutions:
+                h = attnblock(idx, plan[idx][1], h)
+                idx += 1
+            hs.append(h)
+        if lvl != nres - 1:
+            hs.append(resblock(idx, plan[idx][1], hs[-1]))
+            idx += 1
+    h = hs[-1]
+    h = resblock(idx, plan[idx][1], h); idx += 1
+    h = attnblock(idx, plan[idx][1], h); idx += 1
+    h = resblock(idx, plan[idx][1], h); idx += 1
+    for lvl in reversed(range(nres)):
+        for _ in range(cfg.num_res_blocks + 1):
+            h = resblock(idx, plan[idx][1], h, hs.pop())
+            idx += 1
+        if h.H in cfg.attn_resolutions:
+            h = attnblock(idx, plan[idx][1], h)
+            idx += 1
+        if lvl != 0:
+            h = resblock(idx, plan[idx][1], h)
+            idx += 1
+    assert not hs
+    C = h.C
+    a = prog.tensor("out.a", B * S * S * C, "bf16")
+    prog.gn_apply(src0=h.t, stats0=h.stats, C0=C, P0=h.P, gamma=prog.const_f32("out.gn.w", P(idx, "weight")),
+                  beta=prog.const_f32("out.gn.b", P(idx, "bias")), B=B, H=S, W=S, groups=_groups(C), eps=1e-6,
+                  silu=1, out_bf16=a)
+    idx += 1
+    prog.conv_out(a, prog.const_f32("out.w", pack_conv_out(P(idx, "weight"))), prog.const_f32("out.b", P(idx, "bias")),
+                  B, S, S, C, cfg.num_channels)
+    idx += 1
+    assert idx == len(plan)
+    prog.meta.update(model="ncsnpp", out_channels=cfg.num_channels, cond="999*t")
+    return prog

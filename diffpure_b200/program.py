@@ -1,0 +1,142 @@
+"""Abstract program: the score-model UNet lowered to the engine's fused ops.
+
+The lowering (diffpure_b200/lowering_*.py) emits device tensors and ops into a `Program`; the engine
+backend (diffpure_b200/engine.py) materialises it through the C ABI (include/diffpure_b200.h). The op
+records mirror the C descriptor structs one to one, so the same program can be replayed by the CPU
+interpreter used in the host-logic tests.
+"""
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple
+
+
+@dataclass
+class Tensor:
+    """A device tensor. `init` (torch tensor) marks constants (weights, tables) uploaded once."""
+    name: str
+    numel: int
+    dtype: str                      # 'f32' | 'bf16'
+    init: Any = None
+    index: int = -1
+
+    @property
+    def nbytes(self):
+        return self.numel * (4 if self.dtype == "f32" else 2)
+
+
+@dataclass
+class View:
+    """`tensor` seen from an element offset (pointer arithmetic on the device)."""
+    tensor: Tensor
+    offset: int = 0
+
+
+def view(t, offset=0):
+    if t is None:
+        return None
+    if isinstance(t, View):
+        return View(t.tensor, t.offset + offset)
+    return View(t, offset)
+
+
+@dataclass
+class ASeg:
+    act: View          # bf16 NHWC [B,Hin,Win,c_total] (plain GEMM: [rows, c_total])
+    C: int
+    c_total: int
+    taps: int = 1
+    stride: int = 1
+    pad: int = 0
+
+
+@dataclass
+class Op:
+    kind: str
+    args: Dict[str, Any] = field(default_factory=dict)
+
+
+class Program:
+    def __init__(self, batch, height, width):
+        self.B, self.H, self.W = batch, height, width
+        self.tensors: List[Tensor] = []
+        self.ops: List[Op] = []
+        self.meta: Dict[str, Any] = {}
+
+    # -- tensors --------------------------------------------------------------------------------
+    def tensor(self, name, numel, dtype, init=None):
+        t = Tensor(name, int(numel), dtype, init, len(self.tensors))
+        self.tensors.append(t)
+        return t
+
+    def const_f32(self, name, value):
+        return self.tensor(name, value.numel(), "f32", value.detach().float().contiguous().reshape(-1))
+
+    def const_bf16(self, name, value):
+        return self.tensor(name, value.numel(), "bf16", value.detach().float().contiguous().reshape(-1))
+
+    # -- ops ------------------------------------------------------------------------------------
+    def add(self, kind, **args):
+        self.ops.append(Op(kind, args))
+
+    def embed(self, out, B, dim, cos_first, half_minus_1):
+        self.add("embed", out=view(out), B=B, dim=dim, cos_first=cos_first, half_minus_1=half_minus_1)
+
+    def gemm(self, a: List[ASeg], w, w_rows, w_pitch, B, H, W, N, *, batch=1, a_batch_rows=0, b_batch_rows=0,
+             out_batch_stride=0, bias=None, bias_along_m=0, rowvec=None, rowvec_ld=0, rowvec_rows_per_sample=1,
+             rowscale=None, resid=None, alpha=1.0, silu=0, out_f32=None, out_bf16=None, ldc=None, stats=None,
+             softmax=0, softmax_scale=1.0, rowsum_out=None):
+        self.add("gemm", a=a, w=view(w), w_rows=w_rows, w_pitch=w_pitch, B=B, H=H, W=W, N=N, batch=batch,
+                 a_batch_rows=a_batch_rows, b_batch_rows=b_batch_rows, out_batch_stride=out_batch_stride,
+                 bias=view(bias), bias_along_m=bias_along_m, rowvec=view(rowvec), rowvec_ld=rowvec_ld,
+                 rowvec_rows_per_sample=rowvec_rows_per_sample, rowscale=view(rowscale), resid=view(resid),
+                 alpha=float(alpha), silu=silu, out_f32=view(out_f32), out_bf16=view(out_bf16),
+                 ldc=N if ldc is None else ldc, stats=view(stats), softmax=softmax,
+                 softmax_scale=float(softmax_scale), rowsum_out=view(rowsum_out))
+
+    def gn_apply(self, *, src0, stats0, C0, P0, gamma, beta, B, H, W, groups, eps, silu, out_bf16, src1=None,
+                 stats1=None, C1=0, P1=0, film=None, film_ld=0, resample=0, raw_bf16=None, raw_f32=None):
+        self.add("gn_apply", src0=view(src0), stats0=view(stats0), C0=C0, P0=P0, src1=view(src1),
+                 stats1=view(stats1), C1=C1, P1=P1, gamma=view(gamma), beta=view(beta), film=view(film),
+                 film_ld=film_ld, B=B, H=H, W=W, groups=groups, eps=float(eps), silu=silu, resample=resample,
+                 out_bf16=view(out_bf16), raw_bf16=view(raw_bf16), raw_f32=view(raw_f32))
+
+    def conv_in(self, w, bias, out, stats, B, H, W, Cout):
+        self.add("conv_in", w=view(w), bias=view(bias), out=view(out), stats=view(stats), B=B, H=H, W=W, Cout=Cout)
+
+    def conv_out(self, act, w, bias, B, H, W, C, Cout):
+        self.add("conv_out", act=view(act), w=view(w), bias=view(bias), B=B, H=H, W=W, C=C, Cout=Cout)
+
+    def attn_small(self, qkv, out, B, T, heads, d, scale):
+        self.add("attn_small", qkv=view(qkv), out=view(out), B=B, T=T, heads=heads, d=d, scale=float(scale))
+
+    # -- analysis -------------------------------------------------------------------------------
+    def views_of(self, op):
+        """All (View, is_written) operands of an op, for liveness analysis."""
+        out = []
+        for k, v in op.args.items():
+            if isinstance(v, View):
+                out.append(v)
+            elif k == "a":
+                out.extend(seg.act for seg in v)
+        return out
+
+    def last_use(self):
+        last = {}
+        for i, op in enumerate(self.ops):
+            for v in self.views_of(op):
+                last[v.tensor.index] = i
+        return last
+
+    def first_use(self):
+        first = {}
+        for i, op in enumerate(self.ops):
+            for v in self.views_of(op):
+                first.setdefault(v.tensor.index, i)
+        return first
+
+
+def stats_rows(B, HW):
+    """Rows of a [rows][C][2] GroupNorm partial-statistics tensor written by a GEMM epilogue or conv_in."""
+    if HW >= 128:
+        return B * (HW // 128), HW // 128
+    ipt = 128 // HW
+    return ((B + ipt - 1) // ipt) * ipt, 1

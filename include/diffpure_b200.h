@@ -1,0 +1,187 @@
+/* diffpure_b200.h -- C ABI of the B200-native diffusion-purification engine (libdiffpure_b200.so).
+ *
+ * The reference (NVlabs/DiffPure) has no FFI: its hot path is reached through Python classes
+ * (runners/diffpure_sde.py:150-247 RevGuidedDiffusion / RevVPSDE, runners/diffpure_guided.py:17-89
+ * GuidedDiffusion, runners/diffpure_ddpm.py:57-142 Diffusion, called by eval_sde_adv.py:68-93
+ * SDE_Adv_Model.forward). This header is the boundary those runner classes bind instead of calling
+ * torch modules: plain pointers and sizes, no torch types, integer return codes (0 = ok), no C++
+ * exceptions across the ABI; the message of the last failure is returned by dp_last_error().
+ *
+ * Model: an engine owns device buffers and a *program* -- the score-model UNet lowered by the host
+ * (diffpure_b200/lowering.py) to a sequence of fused sm_100a kernels -- for one fixed batch size.
+ *   dp_op_embed      <- timestep embedding        (score_sde/models/layers.py:515-529, guided_diffusion/nn.py:111-129,
+ *                                                   ddpm/unet_ddpm.py:14-32)
+ *   dp_op_gemm       <- every conv3x3 / conv1x1 / NIN / Linear / attention matmul as a tcgen05 implicit GEMM
+ *                       (score_sde/models/layers.py:100-124,546-555; layerspp.py:75-91,242-274;
+ *                        guided_diffusion/unet.py:151-362; ddpm/unet_ddpm.py:63-197)
+ *   dp_op_gn_apply   <- GroupNorm + SiLU (+ FiLM, + nearest-up / 2x2-mean-down, + channel concat)
+ *                       (layerspp.py:219,231,245-258; unet.py:244-260; nn.py:25-27; unet_ddpm.py:40-41,55-60)
+ *   dp_op_stats      <- GroupNorm statistics of a tensor not produced by dp_op_gemm
+ *   dp_op_conv_in    <- the 3->C input conv        (ncsnpp.py:268, unet.py:486, unet_ddpm.py:229)
+ *   dp_op_conv_out   <- the C->3|6 output conv fused with the per-step update
+ *                       (ncsnpp.py:371-374 + runners/diffpure_sde.py:86-147 + torchsde Euler step;
+ *                        guided_diffusion/gaussian_diffusion.py:240-334,403-447; runners/diffpure_ddpm.py:37-54)
+ *   dp_op_attn_small <- whole-sequence attention for short sequences (T <= 64)
+ * Threading: one engine per (process, device); calls on an engine are stream-ordered and not re-entrant.
+ * Ownership: the caller owns every pointer it passes to dp_unet_forward / dp_purify; the engine owns
+ * buffers obtained from dp_buffer_alloc, its tensor maps and CUDA graphs.
+ */
+#ifndef DIFFPURE_B200_H_
+#define DIFFPURE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dp_engine dp_engine;
+
+#define DP_OK 0
+#define DP_ERR_INVALID 1
+#define DP_ERR_CUDA 2
+#define DP_ERR_STATE 3
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int dp_create(dp_engine** out, int device);
+void dp_destroy(dp_engine* e);
+const char* dp_last_error(const dp_engine* e); /* e may be NULL: error of the last failed dp_create */
+int dp_version(void);
+int dp_device_sm_count(const dp_engine* e);
+
+/* ---- engine-owned device buffers (weights, activations, tables) ------------------------------ */
+int dp_buffer_alloc(dp_engine* e, size_t bytes, int* buf_id);
+void* dp_buffer_ptr(dp_engine* e, int buf_id);
+int dp_buffer_write(dp_engine* e, int buf_id, size_t offset, const void* host_src, size_t bytes);
+int dp_buffer_read(dp_engine* e, int buf_id, size_t offset, void* host_dst, size_t bytes);
+size_t dp_bytes_allocated(const dp_engine* e);
+
+/* ---- program construction (all pointers are device pointers inside engine buffers) ----------- */
+
+/* Timestep embedding of the per-step / per-sample condition -> bf16 [B, dim]. */
+typedef struct {
+  void* out_bf16;   /* [B, dim] */
+  int B, dim;
+  int cos_first;    /* 0: [sin | cos] (DDPM++, ddpm)   1: [cos | sin] (ADM) */
+  int half_minus_1; /* 1: freq_i = exp(-ln(1e4) i/(half-1))   0: /half (ADM) */
+} dp_embed_desc;
+
+/* One K segment of the implicit-GEMM A operand. */
+typedef struct {
+  const void* act_bf16; /* NHWC bf16 [B, Hin, Win, c_total]; plain GEMM: [rows, c_total] with Hin = 1 */
+  int C;                /* channels read (multiple of 64) */
+  int c_total;          /* channel pitch of the tensor */
+  int taps;             /* 1 or 9 */
+  int stride;           /* 1, or 2 (pad right/bottom, ddpm/unet_ddpm.py:63-82) */
+  int pad;              /* 1 for 'same' 3x3, else 0 */
+} dp_gemm_aseg;
+
+typedef struct {
+  dp_gemm_aseg a[2];
+  int nseg;
+  const void* w_bf16;   /* [rows, Ktotal] bf16, K contiguous: Ktotal = sum taps*C over segments */
+  long long w_rows;     /* rows of the weight/B matrix visible to the map */
+  long long w_pitch;    /* elements between rows */
+  int B, H, W;          /* output grid (plain GEMM: B = 1, H = 1, W = rows) */
+  int N;                /* output columns (multiple of 8) */
+  int batch;            /* batched GEMM count (attention), else 1 */
+  int a_batch_rows, b_batch_rows;
+  long long out_batch_stride;
+  const float* bias; int bias_along_m;
+  const float* rowvec; int rowvec_ld; int rowvec_rows_per_sample; /* per-sample additive vector */
+  const float* rowscale; /* out *= 1/rowscale[b*M + row] */
+  const float* resid;
+  float alpha; int silu;
+  float* out_f32; void* out_bf16; long long ldc;
+  float* stats;          /* [ceil(M/seg)][N][2] partial (sum, sumsq), seg = min(H*W,128); or NULL */
+  int softmax; float softmax_scale; float* rowsum_out;
+} dp_gemm_desc;
+
+typedef struct {
+  const float* src0; const float* stats0; int C0; int P0; /* fp32 NHWC + [B][P0][C0][2] partials */
+  const float* src1; const float* stats1; int C1; int P1; /* optional channel-concat second source */
+  const float* gamma; const float* beta;                  /* [C0+C1] */
+  const float* film; int film_ld;                         /* optional [B, film_ld]: scale = [:C], shift = [C:2C] */
+  int B, H, W;            /* input grid */
+  int groups; float eps;
+  int silu;
+  int resample;           /* 0 none, 1 nearest x2, 2 2x2 mean */
+  void* out_bf16;         /* [B, H', W', C] normalised (+SiLU) */
+  void* raw_bf16;         /* optional: resampled raw input as bf16 (1x1 shortcut operand) */
+  float* raw_f32;         /* optional: resampled raw input as fp32 (identity residual after resample) */
+} dp_gn_desc;
+
+typedef struct {
+  const float* src; int B, HW, C; /* fp32 [B, HW, C] */
+  float* stats;                   /* [B][P][C][2], P = ceil(HW/128) */
+} dp_stats_desc;
+
+typedef struct {
+  const float* w;    /* [27][Cout] fp32: ((ky*3+kx)*3 + ci) major */
+  const float* bias; /* [Cout] */
+  float* out;        /* fp32 NHWC [B,H,W,Cout] */
+  float* stats;      /* optional per-channel partials of `out` ([B][P][Cout][2]) */
+  int B, H, W, Cout;
+} dp_conv_in_desc;
+
+typedef struct {
+  const void* act_bf16; /* [B,H,W,C] */
+  const float* w;       /* [9][C][Cout] fp32 */
+  const float* bias;    /* [Cout] */
+  int B, H, W, C, Cout; /* Cout = 3 or 6 */
+} dp_conv_out_desc;
+
+typedef struct {
+  const void* qkv_bf16; /* [B*T, 3*heads*d]: q | k | v, each [heads][d] */
+  void* out_bf16;       /* [B*T, heads*d] */
+  int B, T, heads, d;
+  float scale;          /* applied to q.k before softmax */
+} dp_attn_small_desc;
+
+int dp_op_embed(dp_engine* e, const dp_embed_desc* d);
+int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d);
+int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d);
+int dp_op_stats(dp_engine* e, const dp_stats_desc* d);
+int dp_op_conv_in(dp_engine* e, const dp_conv_in_desc* d);
+int dp_op_conv_out(dp_engine* e, const dp_conv_out_desc* d);
+int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d);
+int dp_program_size(const dp_engine* e);
+
+/* Freeze the program for images of [B, C=3, H, W]; captures the CUDA graphs. */
+int dp_finalize(dp_engine* e, int B, int H, int W);
+
+/* ---- execution ------------------------------------------------------------------------------- */
+
+/* One UNet evaluation: x [B,3,H,W] fp32 (device), cond [B] fp32 (device; DDPM++: 999*t, ADM/ddpm: timestep),
+ * out [B,Cout,H,W] fp32 (device). Mirrors model(x, t) of the reference modules. */
+int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float* out_nchw, void* stream);
+
+#define DP_UPDATE_LINEAR 0 /* x <- c[0]*x + c[1]*eps + c[2]*z                 (VP-SDE Euler-Maruyama; ddpm fixed-var) */
+#define DP_UPDATE_LEARNED_RANGE 1 /* guided_diffusion p_sample with learned-range variance and x0 clamp; 8 coefs */
+
+typedef struct {
+  int steps;
+  int update_kind;
+  int ncoef;            /* coefficients per step (3 or 8) */
+  const float* cond;    /* host [steps]: UNet condition of step k (same for the whole batch) */
+  const float* coef;    /* host [steps][ncoef] */
+  float init_scale_x;   /* forward diffusion x = init_scale_x * x0 + init_scale_e * e  */
+  float init_scale_e;
+  const float* init_noise;  /* device [B,3,H,W] or NULL -> counter-based generator */
+  const float* step_noise;  /* device [steps,B,3,H,W] standard normals or NULL -> counter-based generator */
+  uint64_t seed;
+  uint64_t sample_offset;   /* global index of sample 0 (multi-GPU sharding keeps streams identical) */
+} dp_purify_params;
+
+/* The whole purification loop on the device: forward-diffuse, then `steps` x (UNet + fused update).
+ * x0, out: [B,3,H,W] fp32 device, values in [-1,1] (runners/diffpure_sde.py:197-247). */
+int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_purify_params* p, void* stream);
+
+/* Number of kernels one UNet evaluation launches (for bench accounting). */
+int dp_launches_per_eval(const dp_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFPURE_B200_H_ */

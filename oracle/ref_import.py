@@ -1,0 +1,79 @@
+"""Import the *reference's own* Python modules from /root/reference -- build-container only.
+
+Used to pin the oracle restatements (oracle/check_against_reference.py) and to generate the committed
+golden vectors (oracle/make_golden.py). The GPU box has no /root/reference: nothing that runs there
+may import this module.
+
+Third-party packages the reference imports but that are absent offline are replaced by inert stubs
+(SURVEY.md section 8c): torchsde, torchdiffeq, autoattack, robustbench, lmdb, matplotlib.
+"""
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+REF_ROOT = os.environ.get("DIFFPURE_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "runners"))
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install(euler_shim=None):
+    """Put the reference on sys.path with stubs for its missing third-party imports."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    ts = _stub("torchsde")
+    if euler_shim is not None:
+        ts.sdeint_adjoint = euler_shim
+        ts.sdeint = euler_shim
+    if not hasattr(ts, "BrownianInterval"):
+        ts.BrownianInterval = lambda **kw: None
+    _stub("torchdiffeq", odeint_adjoint=None, odeint=None)
+    _stub("autoattack", AutoAttack=object)
+    rb = _stub("robustbench")
+    rb.load_model = lambda *a, **k: None
+    _stub("lmdb")
+    mpl = _stub("matplotlib")
+    mpl.use = lambda *a, **k: None
+    _stub("matplotlib.pyplot")
+    os.environ.setdefault("TORCH_EXTENSIONS_DIR", "/tmp/torch_extensions_ref")
+
+
+def to_namespace(d):
+    if isinstance(d, dict):
+        return SimpleNamespace(**{k: to_namespace(v) for k, v in d.items()})
+    return d
+
+
+def load_config(name):
+    import yaml
+    with open(os.path.join(REF_ROOT, "configs", name)) as f:
+        return to_namespace(yaml.safe_load(f))
+
+
+def build_ncsnpp(overrides=None):
+    """Reference NCSNpp (score_sde/models/ncsnpp.py) on CPU. First import JIT-builds score_sde/op (~2 min)."""
+    install()
+    from score_sde.models import ncsnpp  # noqa: F401  (registers the model)
+    from score_sde.models import utils as mutils
+    cfg = load_config("cifar10.yml")
+    if overrides:
+        for k, v in overrides.items():
+            tgt, key = (cfg.data, k[5:]) if k.startswith("data.") else (cfg.model, k)
+            setattr(tgt, key, v)
+    import torch
+    cfg.device = torch.device("cpu")
+    model = mutils.create_model(cfg)
+    return model.eval(), cfg

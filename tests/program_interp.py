@@ -1,0 +1,216 @@
+"""CPU interpreter of an engine `Program` -- test infrastructure.
+
+Replays the op list the lowering emitted with plain torch ops on flat host buffers, following the
+semantics of the CUDA kernels (dp_gemm.cu epilogue order, dp_elem.cu GroupNorm-from-partials, ...).
+With emulate_bf16=False it must reproduce the oracle to fp32 round-off, which proves the lowering
+(topology, operand offsets, weight packing, statistics plumbing) without a GPU; with emulate_bf16=True
+it predicts the tensor-core path's rounding (bf16 operands, fp32 accumulation).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class Interp:
+    def __init__(self, prog, emulate_bf16=False):
+        self.prog = prog
+        self.bf = emulate_bf16
+        self.mem = {}
+        for t in prog.tensors:
+            if t.init is not None:
+                v = t.init.detach().float().reshape(-1).clone()
+                if t.dtype == "bf16" and self.bf:
+                    v = _bf16(v)
+                self.mem[t.index] = v
+            else:
+                self.mem[t.index] = torch.zeros(t.numel)
+        self.out = None
+
+    # -- helpers ----------------------------------------------------------------------------------
+    def flat(self, v):
+        return self.mem[v.tensor.index], v.offset
+
+    def rd(self, v, shape, strides=None):
+        buf, off = self.flat(v)
+        if strides is None:
+            n = 1
+            for s in shape:
+                n *= s
+            return buf[off:off + n].reshape(shape)
+        return torch.as_strided(buf, shape, strides, off)
+
+    def wr(self, v, value, shape, strides):
+        buf, off = self.flat(v)
+        val = _bf16(value) if (self.bf and v.tensor.dtype == "bf16") else value
+        torch.as_strided(buf, shape, strides, off).copy_(val)
+
+    # -- ops --------------------------------------------------------------------------------------
+    def run(self, x_nchw, cond):
+        self.x = x_nchw.float()
+        self.cond = cond.float()
+        for op in self.prog.ops:
+            getattr(self, "op_" + op.kind)(**op.args)
+        return self.out
+
+    def op_embed(self, out, B, dim, cos_first, half_minus_1):
+        half = dim // 2
+        coef = -math.log(10000.0) / (half - 1 if half_minus_1 else half)
+        freq = torch.exp(torch.arange(half, dtype=torch.float32) * coef)
+        arg = self.cond[:, None] * freq[None]
+        e = torch.cat([torch.cos(arg), torch.sin(arg)] if cos_first else [torch.sin(arg), torch.cos(arg)], 1)
+        self.wr(out, e, (B, dim), (dim, 1))
+
+    def _a_matrix(self, seg, B, H, W, b, a_batch_rows):
+        if H == 1 and seg.taps == 1:  # plain GEMM rows
+            x = self.rd(seg.act, (W, seg.C), (seg.c_total, 1))
+            buf, off = self.flat(seg.act)
+            return torch.as_strided(buf, (W, seg.C), (seg.c_total, 1), off + b * a_batch_rows * seg.c_total)
+        s = seg.stride
+        Hin, Win = H * s, W * s
+        x = self.rd(seg.act, (B, Hin, Win, seg.C), (Hin * Win * seg.c_total, Win * seg.c_total, seg.c_total, 1))
+        cols = []
+        k = 3 if seg.taps == 9 else 1
+        for ky in range(k):
+            for kx in range(k):
+                dy, dx = ky - seg.pad, kx - seg.pad
+                patch = torch.zeros(B, H, W, seg.C)
+                for hh in range(H):
+                    yi = hh * s + dy
+                    if yi < 0 or yi >= Hin:
+                        continue
+                    xs = [w * s + dx for w in range(W)]
+                    valid = [i for i, xi in enumerate(xs) if 0 <= xi < Win]
+                    if not valid:
+                        continue
+                    w0, w1 = valid[0], valid[-1] + 1
+                    patch[:, hh, w0:w1] = x[:, yi, xs[w0]:xs[w1 - 1] + 1:s]
+                cols.append(patch.reshape(B * H * W, seg.C))
+        return torch.cat(cols, 1)
+
+    def op_gemm(self, a, w, w_rows, w_pitch, B, H, W, N, batch, a_batch_rows, b_batch_rows, out_batch_stride, bias,
+                bias_along_m, rowvec, rowvec_ld, rowvec_rows_per_sample, rowscale, resid, alpha, silu, out_f32,
+                out_bf16, ldc, stats, softmax, softmax_scale, rowsum_out):
+        M = B * H * W
+        ktot = sum(s.taps * s.C for s in a)
+        for b in range(batch):
+            A = torch.cat([self._a_matrix(s, B, H, W, b, a_batch_rows) for s in a], 1)
+            wbuf, woff = self.flat(w)
+            Wt = torch.as_strided(wbuf, (N, ktot), (w_pitch, 1), woff + b * b_batch_rows * w_pitch)
+            D = A @ Wt.t()
+            if softmax:
+                mx = D.max(dim=1, keepdim=True).values
+                Pm = torch.exp((D - mx) * softmax_scale)
+                if self.bf:
+                    Pm = _bf16(Pm)
+                self.wr(out_bf16, Pm, (M, N), (ldc, 1)) if batch == 1 else None
+                buf, off = self.flat(out_bf16)
+                torch.as_strided(buf, (M, N), (ldc, 1), off + b * out_batch_stride).copy_(Pm)
+                rbuf, roff = self.flat(rowsum_out)
+                rbuf[roff + b * M: roff + (b + 1) * M] = Pm.sum(1)
+                continue
+            if rowscale is not None:
+                rbuf, roff = self.flat(rowscale)
+                D = D / rbuf[roff + b * M: roff + (b + 1) * M][:, None]
+            if bias is not None:
+                bb, boff = self.flat(bias)
+                D = D + (bb[boff:boff + M][:, None] if bias_along_m else bb[boff:boff + N][None, :])
+            if rowvec is not None:
+                rv, rvo = self.flat(rowvec)
+                nsamp = M // rowvec_rows_per_sample
+                tab = torch.as_strided(rv, (nsamp, N), (rowvec_ld, 1), rvo)
+                D = D + tab.repeat_interleave(rowvec_rows_per_sample, 0)
+            if silu:
+                D = F.silu(D)
+            if resid is not None:
+                rb, ro = self.flat(resid)
+                D = D + torch.as_strided(rb, (M, N), (ldc, 1), ro + b * out_batch_stride)
+            D = D * alpha
+            for dst in (out_f32, out_bf16):
+                if dst is not None:
+                    buf, off = self.flat(dst)
+                    val = _bf16(D) if (self.bf and dst.tensor.dtype == "bf16") else D
+                    torch.as_strided(buf, (M, N), (ldc, 1), off + b * out_batch_stride).copy_(val)
+            if stats is not None:
+                seg = min(H * W, 128)
+                nseg = M // seg
+                Ds = D.reshape(nseg, seg, N)
+                st = torch.stack([Ds.sum(1), (Ds * Ds).sum(1)], -1)  # [nseg, N, 2]
+                sb, so = self.flat(stats)
+                sb[so: so + st.numel()] = st.reshape(-1)
+
+    def op_gn_apply(self, src0, stats0, C0, P0, src1, stats1, C1, P1, gamma, beta, film, film_ld, B, H, W, groups,
+                    eps, silu, resample, out_bf16, raw_bf16, raw_f32):
+        C = C0 + C1
+        HW = H * W
+        xs = [self.rd(src0, (B, H, W, C0))]
+        sums = [self.rd(stats0, (B, P0, C0, 2)).sum(1)]
+        if src1 is not None:
+            xs.append(self.rd(src1, (B, H, W, C1)))
+            sums.append(self.rd(stats1, (B, P1, C1, 2)).sum(1))
+        x = torch.cat(xs, -1)
+        cs = torch.cat(sums, 1).double()                      # [B, C, 2]
+        cpg = C // groups
+        gsum = cs.reshape(B, groups, cpg, 2).sum(2)
+        n = cpg * HW
+        mean = gsum[..., 0] / n
+        var = (gsum[..., 1] / n - mean * mean).clamp_min(0)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        g, bt = self.rd(gamma, (C,)), self.rd(beta, (C,))
+        sc = g[None] * rstd.float().repeat_interleave(cpg, 1)
+        sh = bt[None] - mean.float().repeat_interleave(cpg, 1) * sc
+        if film is not None:
+            fb, fo = self.flat(film)
+            f = torch.as_strided(fb, (B, 2 * C), (film_ld, 1), fo)
+            fs = 1.0 + f[:, :C]
+            sc, sh = sc * fs, sh * fs + f[:, C:]
+        y = x * sc[:, None, None, :] + sh[:, None, None, :]
+        if silu:
+            y = F.silu(y)
+        raw = x
+        if resample == 1:
+            y = y.repeat_interleave(2, 1).repeat_interleave(2, 2)
+            raw = raw.repeat_interleave(2, 1).repeat_interleave(2, 2)
+        elif resample == 2:
+            y = y.reshape(B, H // 2, 2, W // 2, 2, C).mean((2, 4))
+            raw = raw.reshape(B, H // 2, 2, W // 2, 2, C).mean((2, 4))
+        Ho, Wo = y.shape[1], y.shape[2]
+        st = (Ho * Wo * C, Wo * C, C, 1)
+        self.wr(out_bf16, y, (B, Ho, Wo, C), st)
+        if raw_bf16 is not None:
+            self.wr(raw_bf16, raw, (B, Ho, Wo, C), st)
+        if raw_f32 is not None:
+            self.wr(raw_f32, raw, (B, Ho, Wo, C), st)
+
+    def op_conv_in(self, w, bias, out, stats, B, H, W, Cout):
+        wt = self.rd(w, (3, 3, 3, Cout)).permute(3, 2, 0, 1).contiguous()   # [(ky,kx,ci), co] -> [co, ci, ky, kx]
+        y = F.conv2d(self.x, wt, self.rd(bias, (Cout,)), padding=1).permute(0, 2, 3, 1).contiguous()
+        self.wr(out, y, (B, H, W, Cout), (H * W * Cout, W * Cout, Cout, 1))
+        if stats is not None:
+            HW = H * W
+            P = (HW + 127) // 128
+            yy = y.reshape(B, HW, Cout)
+            st = torch.zeros(B, P, Cout, 2)
+            for p in range(P):
+                blk = yy[:, p * 128:(p + 1) * 128]
+                st[:, p, :, 0] = blk.sum(1)
+                st[:, p, :, 1] = (blk * blk).sum(1)
+            sb, so = self.flat(stats)
+            sb[so:so + st.numel()] = st.reshape(-1)
+
+    def op_conv_out(self, act, w, bias, B, H, W, C, Cout):
+        a = self.rd(act, (B, H, W, C)).permute(0, 3, 1, 2)
+        wt = self.rd(w, (3, 3, C, Cout)).permute(3, 2, 0, 1).contiguous()
+        self.out = F.conv2d(a, wt, self.rd(bias, (Cout,)), padding=1)
+
+    def op_attn_small(self, qkv, out, B, T, heads, d, scale):
+        x = self.rd(qkv, (B, T, 3, heads, d))
+        q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]                        # [B, T, heads, d]
+        s = torch.einsum("bihd,bjhd->bhij", q, k) * scale
+        p = torch.softmax(s, -1)
+        o = torch.einsum("bhij,bjhd->bihd", p, v).reshape(B, T, heads * d)
+        self.wr(out, o, (B, T, heads * d), (T * heads * d, heads * d, 1))
