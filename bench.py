@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- purified images/sec of the DiffPure reverse-SDE hot path on B200 (BASELINE.json metric).
+
+Workload (configs[1]): CIFAR-10 32x32 DDPM++ (score_sde NCSN++, configs/cifar10.yml), VP-SDE t*=0.1 ->
+100 Euler-Maruyama steps, batch 512 per GPU, random-init weights (seeded factory), synthetic images.
+One "step" of this benchmark = one whole purification of one batch (100 UNet evaluations + fused updates).
+
+  value      images/s with inputs resident in HBM (dp_purify through the C ABI), max-over-ranks device time
+  e2e        the same through the reference-facing runner API (RevGuidedDiffusion.image_editing_sample)
+             from pinned host memory and back (H2D + D2H inside the timed region)
+  roofline   dominant kernel = the tcgen05 implicit-GEMM kernel: algorithmic FLOPs / CUDA-event time of its
+             launches (per-op events on the engine stream) vs the measured bf16 peak
+  cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample
+
+`--impl reference` times the reference's algorithm on the host cores (oracle port; the reference itself is
+Python + an unvendored torchsde and cannot travel to the GPU box).
+N > 1: one process per GPU (torchrun), weights broadcast once over NCCL, batch sharded, one all_gather of
+the purified images per step; no collective inside the SDE loop. Scaling is weak (512 images per GPU).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+F_PER_IMAGE_EVAL = 37.09e9   # algorithmic FLOPs / image / UNet eval, DDPM++
+T_STAR = 100
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", p.get("bf16_tflops")), p.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md: 1.4 PF/s sustained, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        hot = [v for v in sm if v > 500] or sm
+        return {"sm_mhz": statistics.median(hot) if hot else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_weights(seed=0):
+    from diffpure_b200 import lowering_ncsnpp as L, synthetic
+    cfg = L.cifar10_cfg()
+    return cfg, synthetic.random_state_dict(L.param_shapes(cfg), seed=seed)
+
+
+def cpu_reference_rate(batch, steps, threads=None):
+    """Oracle (CPU port of the reference loop) on a bounded sample: `batch` images, `steps` of the 100 Euler steps."""
+    from oracle import ncsnpp as O, sde as OS, weights
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = O.CIFAR10_CFG
+    sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
+    e0 = torch.randn(batch, 3, 32, 32, generator=g)
+    grid = OS.time_grid(T_STAR)
+    x = OS.forward_diffuse(x0, e0, T_STAR)
+    unet = lambda xx, tt: O.forward(cfg, sd, xx, tt)  # noqa: E731
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for k in range(steps):
+            t, tn = grid[k], grid[k + 1]
+            h = tn - t
+            f = OS.rev_vpsde_f(unet, "score_sde", t, x)
+            gk = OS.rev_vpsde_g(t, batch)[:, None, None, None]
+            x = x + f * h + gk * torch.randn(x.shape, generator=g) * torch.sqrt(h)
+        dt = time.perf_counter() - t0
+    full = dt * (len(grid) - 1) / steps
+    return batch / full, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    batch, sub = 8, 4
+    for i in range(args.warmup + args.steps):
+        rate, dt, threads = cpu_reference_rate(batch, sub)
+        if i >= args.warmup:
+            vals.append((rate, dt))
+    rate = statistics.mean(v[0] for v in vals)
+    ms = statistics.mean(v[1] for v in vals) * 1e3 * (100 / sub)
+    sample = f"oracle CPU port, batch {batch}, {sub} of 100 Euler steps, extrapolated linearly, {threads} threads"
+    line = {"impl": "reference", "metric": "purified images/sec (100-step VP-SDE)", "value": rate, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CIFAR-10 32x32 DDPM++ VP-SDE t*=0.1, 100 Euler steps (CPU sample: batch 8)",
+                       "weights": "random-init (seeded)"},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 GPU (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from diffpure_b200 import lowering_ncsnpp as L, schedule
+    from diffpure_b200.engine import Engine
+    from diffpure_b200.runners.diffpure_sde import RevGuidedDiffusion
+    from types import SimpleNamespace
+
+    B = args.batch
+    # ---- weights: rank 0 materialises them, one NCCL broadcast of the flat blob --------------------------
+    cfg, sd = make_weights(seed=0)
+    if world > 1:
+        names = list(sd.keys())
+        flat = torch.cat([sd[k].reshape(-1) for k in names]).to(dev)
+        if rank != 0:
+            flat.zero_()
+        dist.broadcast(flat, src=0)
+        off, flat_cpu = 0, flat.cpu()
+        for k in names:
+            n = sd[k].numel()
+            sd[k] = flat_cpu[off:off + n].reshape(sd[k].shape).clone()
+            off += n
+    eng = Engine(L.lower(cfg, sd, B), device=local)
+    cond, coef = schedule.vpsde_tables(T_STAR)
+    nsteps = len(cond)
+    sx, se = schedule.vpsde_forward_scales(T_STAR)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    x_host = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory()
+    x_dev = x_host.to(dev)
+    gathered = [torch.empty_like(x_dev) for _ in range(world)] if world > 1 else None
+
+    def one_step(seed):
+        out = eng.purify(x_dev, cond, coef, sx, se, seed=seed, sample_offset=rank * B)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(1000 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        one_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(one_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- e2e through the runner API from pinned host memory ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        rargs = SimpleNamespace(t=T_STAR, rand_t=False, t_delta=15, use_bm=False, score_type="score_sde",
+                                sample_step=1, log_dir="/tmp/diffpure_b200_bench", save_images=False)
+        rconfig = SimpleNamespace(data=SimpleNamespace(dataset="CIFAR10", image_size=32, num_channels=3),
+                                  model=SimpleNamespace(name="ncsnpp", resblock_type="biggan", fir=False,
+                                                        skip_rescale=True, progressive="none",
+                                                        progressive_input="none", embedding_type="positional",
+                                                        conditional=True, nonlinearity="swish", nf=cfg.nf,
+                                                        ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks,
+                                                        attn_resolutions=list(cfg.attn_resolutions)),
+                                  device=dev)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            runner = RevGuidedDiffusion(rargs, rconfig, device=dev, state_dict=sd)
+        runner.model._engines[(B, local)] = eng     # share the engine already built for this batch size
+        runner.sample_offset = rank * B
+        out_host = torch.empty(B, 3, 32, 32).pin_memory()
+
+        def e2e_step(seed):
+            with torch.no_grad():
+                out = runner.image_editing_sample(x_host.to(dev, non_blocking=True), bs_id=2, tag="bench", seed=seed)
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_step(0)
+        ms_e2e = timed(e2e_step, args.steps)
+        e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s",
+               "h2d_bytes_per_step": B * 3 * 32 * 32 * 4, "d2h_bytes_per_step": B * 3 * 32 * 32 * 4,
+               "api": "diffpure_b200.runners.diffpure_sde.RevGuidedDiffusion.image_editing_sample"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-op CUDA events on the engine stream) ------------------------
+    peak_tf, peak_gbs, peak_src = load_peaks()
+    prof = None
+    for _ in range(3):
+        prof = eng.profile_ops(mode=1)
+    by_kind = {}
+    for kind, ms, fl in prof:
+        d = by_kind.setdefault(kind, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += ms
+        d[2] += fl
+    gemm_n, gemm_ms, gemm_fl = by_kind["gemm"]
+    eval_ms = sum(v[1] for v in by_kind.values())
+    alg_flops_eval = F_PER_IMAGE_EVAL * B
+    achieved_tf = alg_flops_eval / (gemm_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "dp::gemm_kernel<BN,softmax> (tcgen05 implicit GEMM)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None, "peak_source": peak_src, "launches_per_eval": gemm_n,
+                "avg_launch_ms": gemm_ms / gemm_n, "alg_flops_per_launch": alg_flops_eval / gemm_n,
+                "executed_gemm_flops_per_eval": gemm_fl, "kernel_share_of_eval": gemm_ms / eval_ms,
+                "eval_ms_by_kind": {k: round(v[1], 4) for k, v in by_kind.items()},
+                "whole_loop_frac_of_peak": (value / world) * nsteps * F_PER_IMAGE_EVAL / 1e12 / peak_tf}
+    traffic_path = os.path.join(ROOT, "profiles", "gemm_dram_bytes_per_launch.json")
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, dt, threads = cpu_reference_rate(8, 4)
+        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"oracle CPU port of the reference loop, batch 8, 4 of 100 Euler steps ({dt:.1f} s), "
+                         f"extrapolated linearly"}
+
+    launches = args.steps * (nsteps * (eng.launches_per_eval + 1) + 2)
+    line = {"metric": "purified images/sec (100-step VP-SDE)", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "CIFAR-10 32x32 DDPM++ VP-SDE t*=0.1, 100 Euler steps, batch %d per GPU" % B,
+                       "weights": "random-init (seeded factory)", "global_batch": world * B,
+                       "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (>= 2 GB of activations) exceeds the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

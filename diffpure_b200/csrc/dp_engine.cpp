@@ -110,54 +110,58 @@ int ensure_run_state(dp_engine* e) {
   return DP_OK;
 }
 
-// mode: 0 = forward graph (per-sample cond, eps to eps_out), 1 = step graph (tables, fused update)
-int run_ops(dp_engine* e, int mode, cudaStream_t s) {
-  for (size_t i = 0; i < e->ops.size(); ++i) {
-    Op& op = e->ops[i];
-    int rc = 0;
-    switch (op.kind) {
-      case OP_EMBED: {
-        dp::EmbedParams p = op.embed;
-        p.cond_per_sample = mode == 0 ? e->cond_per_sample : nullptr;
-        rc = dp::launch_embed(p, s);
-        break;
-      }
-      case OP_GEMM:
-        rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s);
-        break;
-      case OP_GN:
-        rc = dp::launch_gn_apply(op.gn, e->num_sms, s);
-        break;
-      case OP_STATS:
-        rc = dp::launch_stats(op.stats.src, op.stats.stats, op.stats.B, op.stats.HW, op.stats.C, s);
-        break;
-      case OP_STATS_REDUCE:
-        rc = dp::launch_stats_reduce(op.sred.in, op.sred.out, op.sred.B, op.sred.P, op.sred.C, s);
-        break;
-      case OP_CONV_IN: {
-        dp::ConvInParams p = op.cin;
-        p.x = e->x_state;
-        rc = dp::launch_conv_in(p, s);
-        break;
-      }
-      case OP_CONV_OUT: {
-        dp::ConvOutParams p = op.cout_;
-        p.mode = mode;
-        p.out_nchw = e->eps_out;
-        p.x = e->x_state;
-        p.call = e->d_call;
-        rc = dp::launch_conv_out(p, s);
-        break;
-      }
-      case OP_ATTN_SMALL:
-        rc = dp::launch_attn_small(op.attn, s);
-        break;
+// mode: 0 = forward (per-sample cond, eps to eps_out), 1 = step (per-step tables, fused state update)
+int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
+  Op& op = e->ops[i];
+  int rc = 0;
+  switch (op.kind) {
+    case OP_EMBED: {
+      dp::EmbedParams p = op.embed;
+      p.cond_per_sample = mode == 0 ? e->cond_per_sample : nullptr;
+      rc = dp::launch_embed(p, s);
+      break;
     }
-    if (rc != 0)
-      return fail(e, DP_ERR_CUDA,
-                  "launch of op " + std::to_string(i) + " (kind " + std::to_string(op.kind) +
-                      ") failed: " + cudaGetErrorString(static_cast<cudaError_t>(rc)));
+    case OP_GEMM:
+      rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s);
+      break;
+    case OP_GN:
+      rc = dp::launch_gn_apply(op.gn, e->num_sms, s);
+      break;
+    case OP_STATS:
+      rc = dp::launch_stats(op.stats.src, op.stats.stats, op.stats.B, op.stats.HW, op.stats.C, s);
+      break;
+    case OP_STATS_REDUCE:
+      rc = dp::launch_stats_reduce(op.sred.in, op.sred.out, op.sred.B, op.sred.P, op.sred.C, s);
+      break;
+    case OP_CONV_IN: {
+      dp::ConvInParams p = op.cin;
+      p.x = e->x_state;
+      rc = dp::launch_conv_in(p, s);
+      break;
+    }
+    case OP_CONV_OUT: {
+      dp::ConvOutParams p = op.cout_;
+      p.mode = mode;
+      p.out_nchw = e->eps_out;
+      p.x = e->x_state;
+      p.call = e->d_call;
+      rc = dp::launch_conv_out(p, s);
+      break;
+    }
+    case OP_ATTN_SMALL:
+      rc = dp::launch_attn_small(op.attn, s);
+      break;
   }
+  if (rc != 0)
+    return fail(e, DP_ERR_CUDA,
+                "launch of op " + std::to_string(i) + " (kind " + std::to_string(op.kind) +
+                    ") failed: " + cudaGetErrorString(static_cast<cudaError_t>(rc)));
+  return DP_OK;
+}
+
+int run_ops(dp_engine* e, int mode, cudaStream_t s) {
+  for (size_t i = 0; i < e->ops.size(); ++i)
+    if (int rc = run_op(e, i, mode, s)) return rc;
   if (mode == 1) {
     int rc = dp::launch_step_advance(e->d_step, s);
     if (rc) return fail(e, DP_ERR_CUDA, "launch_step_advance failed");
@@ -566,6 +570,39 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   if (rc) return fail(e, DP_ERR_CUDA, "nhwc_to_nchw launch failed");
   DP_CUDA(e, cudaStreamSynchronize(s));
   return DP_OK;
+}
+
+int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap) {
+  if (!e || !ms || !kinds || !flops) return DP_ERR_INVALID;
+  if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
+  const int n = static_cast<int>(e->ops.size());
+  if (cap < n) return fail(e, DP_ERR_INVALID, "dp_profile_ops: capacity too small");
+  DP_CUDA(e, cudaSetDevice(e->device));
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& x : ev) DP_CUDA(e, cudaEventCreate(&x));
+  int rc = DP_OK;
+  for (int i = 0; i < n && rc == DP_OK; ++i) {
+    cudaEventRecord(ev[2 * i], e->stream);
+    rc = run_op(e, i, mode, e->stream);
+    cudaEventRecord(ev[2 * i + 1], e->stream);
+  }
+  if (rc == DP_OK) {
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) rc = cuda_fail(e, ce, "dp_profile_ops");
+  }
+  for (int i = 0; i < n && rc == DP_OK; ++i) {
+    cudaEventElapsedTime(&ms[i], ev[2 * i], ev[2 * i + 1]);
+    kinds[i] = static_cast<int>(e->ops[i].kind);
+    flops[i] = 0.0;
+    if (e->ops[i].kind == OP_GEMM) {
+      const dp::GemmParams& g = e->ops[i].gemm;
+      double k = 0;
+      for (int s2 = 0; s2 < g.nseg; ++s2) k += 64.0 * g.a[s2].taps * g.a[s2].kchunks;
+      flops[i] = 2.0 * g.M * g.N * k * g.batch;
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
 }
 
 float dp_normal_host(uint64_t seed, uint64_t sample, uint32_t stream, uint32_t pixel, int c) {

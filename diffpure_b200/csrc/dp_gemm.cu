@@ -20,7 +20,8 @@ namespace {
 
 constexpr int kNumThreads = 256;
 constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kStagingFloats = 4 * 32 * 33;
+constexpr int kStgPitch = 36;  // floats; 144-byte rows keep float4 accesses aligned and conflict-free
+constexpr int kStagingFloats = 4 * 32 * kStgPitch;
 constexpr int kMaxStages = 8;
 
 template <int BN>
@@ -30,8 +31,7 @@ struct Smem {
   static constexpr int kStatsFloats = 8 * BN * 2;
   static constexpr int kBarBytes = 256;
   static constexpr size_t total(int stages) {
-    return 1024 + static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 +
-           kBarBytes;
+    return static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 + kBarBytes;
   }
 };
 
@@ -63,10 +63,10 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 template <int BN, bool kSoftmax>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   using L = Smem<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw;
+  if ((base & 1023u) != 0u) __trap();
 
   const int stages = p.num_stages;
   float* staging = reinterpret_cast<float*>(sm + static_cast<size_t>(stages) * L::kStageBytes);
@@ -179,8 +179,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // TMEM (lane = row) -> registers -> smem [32 rows][36] -> registers (lane = 4 columns x 4 row groups):
+    // every shared/global access below is a conflict-free / fully coalesced 128-bit access.
     const int q = warp - 4;  // TMEM lane quadrant == warp_id % 4
-    float* stg = staging + q * (32 * 33);
+    float* stg = staging + q * (32 * kStgPitch);
+    const int c4 = (lane & 7) * 4;
+    const int rsub = lane >> 3;
+    const bool has_bias_n = p.bias != nullptr && !p.bias_along_m;
+    const bool has_bias_m = p.bias != nullptr && p.bias_along_m;
+    const bool has_rowvec = p.rowvec != nullptr;
+    const bool has_rowscale = p.rowscale != nullptr;
+    const bool has_resid = p.resid != nullptr;
+    const bool has_f32 = p.out_f32 != nullptr;
+    const bool has_bf16 = p.out_bf16 != nullptr;
+    const bool do_silu = p.silu != 0;
+    const bool do_stats = p.stats != nullptr;
+    const float alpha = p.alpha;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -213,26 +227,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
             mbar_arrive(tempty_bar(as));
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = exp2f((__uint_as_float(r[j]) - mx) * sc);
-            const float er = __bfloat162float(__float2bfloat16_rn(e));
-            sum += er;
-            stg[lane * 33 + j] = er;
+          for (int j = 0; j < 8; ++j) {
+            float4 e4;
+            float* e = reinterpret_cast<float*>(&e4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float ev = exp2f((__uint_as_float(r[4 * j + u]) - mx) * sc);
+              e[u] = __bfloat162float(__float2bfloat16_rn(ev));
+              sum += e[u];
+            }
+            *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * j) = e4;
           }
           __syncwarp();
-          const int col = c.nt * BN + ch * 32 + lane;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
+          const int col = c.nt * BN + ch * 32 + c4;
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rr = i8 * 4 + rsub;
             const int row = row0 + rr;
-            if (row < p.M && col < p.N)
-              p.out_bf16[obase + static_cast<long long>(row) * p.ldc + col] =
-                  __float2bfloat16_rn(stg[rr * 33 + lane]);
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgPitch + c4);
+            if (row < p.M && col < p.N) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(p.out_bf16 + obase + static_cast<long long>(row) * p.ldc + col) = pk;
+            }
           }
           __syncwarp();
         }
         if (row0 + lane < p.M) p.rowsum_out[static_cast<long long>(c.b) * p.M + row0 + lane] = sum;
       } else {
-        const bool do_stats = p.stats != nullptr;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           tmem_ld_32x32b_x32(taddr + ch * 32, r);
@@ -243,45 +267,87 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
             mbar_arrive(tempty_bar(as));
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * j) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
-          const int col = c.nt * BN + ch * 32 + lane;
+          const int col = c.nt * BN + ch * 32 + c4;
           const bool colok = col < p.N;
-          const float bias_c = (p.bias != nullptr && !p.bias_along_m && colok) ? p.bias[col] : 0.f;
-          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_bias_n && colok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+          float st[16];  // [half][sum|sumsq][4 cols]
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st[i] = 0.f;
+          // Issue all residual loads of this 32x32 block before any store: `resid` and `out` may alias
+          // from the compiler's point of view, which would otherwise serialise one HBM round trip per row.
+          float4 rs8[8];
+          if (has_resid) {
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const int row = row0 + i8 * 4 + rsub;
+              rs8[i8] = (row < p.M && colok)
+                            ? __ldg(reinterpret_cast<const float4*>(p.resid + obase + static_cast<long long>(row) * p.ldc + col))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rr = i8 * 4 + rsub;
             const int row = row0 + rr;
-            float v = stg[rr * 33 + lane];
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgPitch + c4);
             if (row < p.M && colok) {
-              if (p.rowscale != nullptr)
-                v *= 1.0f / p.rowscale[static_cast<long long>(c.b) * p.M + row];
-              v += bias_c;
-              if (p.bias != nullptr && p.bias_along_m) v += p.bias[row];
-              if (p.rowvec != nullptr)
-                v += p.rowvec[static_cast<long long>(row >> p.rowvec_shift) * p.rowvec_ld + col];
-              if (p.silu) v = silu_f(v);
-              const long long o = obase + static_cast<long long>(row) * p.ldc + col;
-              if (p.resid != nullptr) v += p.resid[o];
-              v *= p.alpha;
-              if (p.out_f32 != nullptr) p.out_f32[o] = v;
-              if (p.out_bf16 != nullptr) p.out_bf16[o] = __float2bfloat16_rn(v);
-              if (rr < 16) {
-                s0 += v;
-                q0 += v * v;
-              } else {
-                s1 += v;
-                q1 += v * v;
+              if (has_rowscale) {
+                const float rinv = 1.0f / p.rowscale[static_cast<long long>(c.b) * p.M + row];
+                v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv;
               }
+              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+              if (has_bias_m) {
+                const float bm = p.bias[row];
+                v.x += bm; v.y += bm; v.z += bm; v.w += bm;
+              }
+              if (has_rowvec) {
+                const float4 rv = *reinterpret_cast<const float4*>(
+                    p.rowvec + static_cast<long long>(row >> p.rowvec_shift) * p.rowvec_ld + col);
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+              }
+              if (do_silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+              const long long o = obase + static_cast<long long>(row) * p.ldc + col;
+              if (has_resid) {
+                const float4 rs = rs8[i8];
+                v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+              }
+              v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+              if (has_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+              if (has_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(p.out_bf16 + o) = pk;
+              }
+              float* h = st + (i8 >= 4 ? 8 : 0);
+              h[0] += v.x; h[1] += v.y; h[2] += v.z; h[3] += v.w;
+              h[4] += v.x * v.x; h[5] += v.y * v.y; h[6] += v.z * v.z; h[7] += v.w * v.w;
             }
           }
           if (do_stats) {
-            float* d0 = sstats + ((2 * q + 0) * BN + ch * 32 + lane) * 2;
-            float* d1 = sstats + ((2 * q + 1) * BN + ch * 32 + lane) * 2;
-            d0[0] = s0;
-            d0[1] = q0;
-            d1[0] = s1;
-            d1[1] = q1;
+            // fold the 4 row groups (lanes l, l+8, l+16, l+24) in a fixed order
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              st[i] += __shfl_xor_sync(0xffffffffu, st[i], 8);
+              st[i] += __shfl_xor_sync(0xffffffffu, st[i], 16);
+            }
+            if (rsub == 0) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float* d = sstats + ((2 * q + hh) * BN + ch * 32 + c4 + u) * 2;
+                  d[0] = st[hh * 8 + u];
+                  d[1] = st[hh * 8 + 4 + u];
+                }
+            }
           }
           __syncwarp();
         }

@@ -212,6 +212,17 @@ class Engine:
         self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), None), "dp_purify")
         return out
 
+    OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "conv_out", "attn_small")
+
+    def profile_ops(self, mode=0):
+        """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""
+        n = self.launches_per_eval
+        ms = (C.c_float * n)()
+        kinds = (C.c_int * n)()
+        flops = (C.c_double * n)()
+        self._check(self.lib.dp_profile_ops(self.h, mode, ms, kinds, flops, n), "dp_profile_ops")
+        return [(self.OP_KINDS[kinds[i]], float(ms[i]), float(flops[i])) for i in range(n)]
+
     def read_tensor(self, name):
         """Debug: copy an engine tensor back to the host (intermediate values need pool=False)."""
         t = next(t for t in self.program.tensors if t.name == name)

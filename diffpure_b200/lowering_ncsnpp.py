@@ -76,6 +76,39 @@ def module_plan(cfg):
     return plan
 
 
+def param_shapes(cfg):
+    """name -> shape of every parameter in the reference's state_dict order (ncsnpp.py:68-230, layerspp.py:212-240)."""
+    shapes = {}
+    temb = 4 * cfg.nf
+    for i, (kind, kw) in enumerate(module_plan(cfg)):
+        p = f"all_modules.{i}."
+        if kind == "lin0":
+            shapes[p + "weight"], shapes[p + "bias"] = (temb, cfg.nf), (temb,)
+        elif kind == "lin1":
+            shapes[p + "weight"], shapes[p + "bias"] = (temb, temb), (temb,)
+        elif kind == "conv_in":
+            shapes[p + "weight"], shapes[p + "bias"] = (cfg.nf, cfg.num_channels, 3, 3), (cfg.nf,)
+        elif kind == "gn_out":
+            shapes[p + "weight"], shapes[p + "bias"] = (kw["c"],), (kw["c"],)
+        elif kind == "conv_out":
+            shapes[p + "weight"], shapes[p + "bias"] = (cfg.num_channels, kw["c"], 3, 3), (cfg.num_channels,)
+        elif kind == "res":
+            cin, cout = kw["cin"], kw["cout"]
+            shapes[p + "GroupNorm_0.weight"], shapes[p + "GroupNorm_0.bias"] = (cin,), (cin,)
+            shapes[p + "Conv_0.weight"], shapes[p + "Conv_0.bias"] = (cout, cin, 3, 3), (cout,)
+            shapes[p + "Dense_0.weight"], shapes[p + "Dense_0.bias"] = (cout, temb), (cout,)
+            shapes[p + "GroupNorm_1.weight"], shapes[p + "GroupNorm_1.bias"] = (cout,), (cout,)
+            shapes[p + "Conv_1.weight"], shapes[p + "Conv_1.bias"] = (cout, cout, 3, 3), (cout,)
+            if cin != cout or kw["mode"] != 0:
+                shapes[p + "Conv_2.weight"], shapes[p + "Conv_2.bias"] = (cout, cin, 1, 1), (cout,)
+        elif kind == "attn":
+            c = kw["c"]
+            shapes[p + "GroupNorm_0.weight"], shapes[p + "GroupNorm_0.bias"] = (c,), (c,)
+            for j in range(4):
+                shapes[p + f"NIN_{j}.W"], shapes[p + f"NIN_{j}.b"] = (c, c), (c,)
+    return shapes
+
+
 def lower(cfg, sd, B):
     """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU)."""
     S = cfg.image_size

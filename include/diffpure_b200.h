@@ -178,6 +178,15 @@ typedef struct {
  * x0, out: [B,3,H,W] fp32 device, values in [-1,1] (runners/diffpure_sde.py:197-247). */
 int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_purify_params* p, void* stream);
 
+/* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
+ * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
+ * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,
+ * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
+int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
+
+/* Host evaluation of the counter-based normal generator (tests). */
+float dp_normal_host(uint64_t seed, uint64_t sample, uint32_t stream, uint32_t pixel, int c);
+
 /* Number of kernels one UNet evaluation launches (for bench accounting). */
 int dp_launches_per_eval(const dp_engine* e);
 
