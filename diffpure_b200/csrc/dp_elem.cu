@@ -140,64 +140,74 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, int ppc) {
   const int Ho = p.resample == 1 ? p.H * 2 : (p.resample == 2 ? p.H / 2 : p.H);
   const int Wo = p.resample == 1 ? p.W * 2 : (p.resample == 2 ? p.W / 2 : p.W);
   const int HWo = Ho * Wo;
-  const int vpp = C / 8;
-  const int p0 = blockIdx.x * ppc;
-  const int total = ppc * vpp;
-  for (int idx = tid; idx < total; idx += blockDim.x) {
-    const int px = p0 + idx / vpp;
-    if (px >= HWo) break;
-    const int c = (idx % vpp) * 8;
-    const float* src;
-    int Cx, cl;
-    if (c < p.C0) { src = p.src0; Cx = p.C0; cl = c; }
-    else          { src = p.src1; Cx = p.C1; cl = c - p.C0; }
-    const int ho = px / Wo, wo = px - ho * Wo;
-    float y[8], r[8];
-    float a8[8], b8[8];
+  const int vpp = C / 8;                 // 8-channel vectors per pixel
+  const int rpi = blockDim.x / vpp;      // pixels per block iteration (blockDim.x is a multiple of vpp)
+  const int c = (tid % vpp) * 8;         // this thread's fixed channel vector
+  const int pr = tid / vpp;
+  float a8[8], b8[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a8[j] = sc[c + j]; b8[j] = sh[c + j]; }
+  for (int j = 0; j < 8; ++j) { a8[j] = sc[c + j]; b8[j] = sh[c + j]; }
+  const float* src;
+  int Cx, cl;
+  if (c < p.C0) { src = p.src0; Cx = p.C0; cl = c; }
+  else          { src = p.src1; Cx = p.C1; cl = c - p.C0; }
+  src += static_cast<size_t>(b) * HW * Cx + cl;
+  const size_t obase = static_cast<size_t>(b) * HWo * C + c;
+  const int p_end = min(HWo, (static_cast<int>(blockIdx.x) + 1) * ppc);
+  const bool act = p.silu != 0;
+#pragma unroll 4
+  for (int px = blockIdx.x * ppc + pr; px < p_end; px += rpi) {
+    float y[8], r[8];
     if (p.resample != 2) {
-      const int hi = p.resample == 1 ? ho >> 1 : ho, wi = p.resample == 1 ? wo >> 1 : wo;
-      const float4* s4 = reinterpret_cast<const float4*>(
-          src + (static_cast<size_t>(b) * HW + static_cast<size_t>(hi) * p.W + wi) * Cx + cl);
-      const float4 v0 = s4[0], v1 = s4[1];
+      int pin = px;
+      if (p.resample == 1) {
+        const int ho = px / Wo, wo = px - ho * Wo;
+        pin = (ho >> 1) * p.W + (wo >> 1);
+      }
+      const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<size_t>(pin) * Cx);
+      const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1);
       r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = r[j] * a8[j] + b8[j];
-        y[j] = p.silu ? silu_f(t) : t;
+        y[j] = act ? silu_f(t) : t;
       }
     } else {
+      const int ho = px / Wo, wo = px - ho * Wo;
+      float4 v[8];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float4* s4 = reinterpret_cast<const float4*>(
+            src + (static_cast<size_t>(2 * ho + (d >> 1)) * p.W + (2 * wo + (d & 1))) * Cx);
+        v[2 * d] = __ldg(s4);
+        v[2 * d + 1] = __ldg(s4 + 1);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { y[j] = 0.f; r[j] = 0.f; }
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+      for (int d = 0; d < 4; ++d) {
+        const float q[8] = {v[2 * d].x, v[2 * d].y, v[2 * d].z, v[2 * d].w,
+                            v[2 * d + 1].x, v[2 * d + 1].y, v[2 * d + 1].z, v[2 * d + 1].w};
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const float4* s4 = reinterpret_cast<const float4*>(
-              src + (static_cast<size_t>(b) * HW + static_cast<size_t>(2 * ho + dy) * p.W + (2 * wo + dx)) * Cx + cl);
-          const float4 v0 = s4[0], v1 = s4[1];
-          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float t = v[j] * a8[j] + b8[j];
-            y[j] += p.silu ? silu_f(t) : t;
-            r[j] += v[j];
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float t = q[j] * a8[j] + b8[j];
+          y[j] += act ? silu_f(t) : t;
+          r[j] += q[j];
         }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { y[j] *= 0.25f; r[j] *= 0.25f; }
     }
-    const size_t o = (static_cast<size_t>(b) * HWo + px) * C + c;
+    const size_t o = obase + static_cast<size_t>(px) * C;
     uint4 pk;
     pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
     pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
     *reinterpret_cast<uint4*>(p.out + o) = pk;
     if (p.raw) {
-      uint4 pr;
-      pr.x = pack_bf16x2(r[0], r[1]); pr.y = pack_bf16x2(r[2], r[3]);
-      pr.z = pack_bf16x2(r[4], r[5]); pr.w = pack_bf16x2(r[6], r[7]);
-      *reinterpret_cast<uint4*>(p.raw + o) = pr;
+      uint4 pq;
+      pq.x = pack_bf16x2(r[0], r[1]); pq.y = pack_bf16x2(r[2], r[3]);
+      pq.z = pack_bf16x2(r[4], r[5]); pq.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(p.raw + o) = pq;
     }
     if (p.raw_f32) {
       float4* d = reinterpret_cast<float4*>(p.raw_f32 + o);
@@ -209,14 +219,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, int ppc) {
 
 int launch_gn_apply(const GnParams& p, int num_sms, cudaStream_t s) {
   const int C = p.C0 + p.C1;
+  const int vpp = C / 8;
+  if (vpp > 256) return static_cast<int>(cudaErrorInvalidValue);
+  const int threads = vpp * (256 / vpp);  // every thread keeps one fixed 8-channel vector
+  const int rpi = threads / vpp;
   const int Ho = p.resample == 1 ? p.H * 2 : (p.resample == 2 ? p.H / 2 : p.H);
   const int Wo = p.resample == 1 ? p.W * 2 : (p.resample == 2 ? p.W / 2 : p.W);
   const int HWo = Ho * Wo;
-  int ppc = 256;
-  while (ppc > 16 && static_cast<long long>(p.B) * ((HWo + ppc - 1) / ppc) < 2LL * num_sms) ppc >>= 1;
+  // pixels per CTA: large enough to amortise the per-CTA statistics prologue, small enough for >= 4 waves
+  int ppc = 512;
+  while (ppc > 16 && ppc > rpi && static_cast<long long>(p.B) * ((HWo + ppc - 1) / ppc) < 4LL * num_sms) ppc >>= 1;
+  if (ppc < rpi) ppc = rpi;
   dim3 grid((HWo + ppc - 1) / ppc, p.B);
   const size_t smem = static_cast<size_t>(2 * C + 2 * p.groups) * sizeof(float);
-  gn_apply_kernel<<<grid, 256, smem, s>>>(p, ppc);
+  gn_apply_kernel<<<grid, threads, smem, s>>>(p, ppc);
   return static_cast<int>(cudaGetLastError());
 }
 

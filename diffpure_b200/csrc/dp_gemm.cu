@@ -60,9 +60,16 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
-template <int BN, bool kSoftmax>
+// Epilogue feature mask. The common combinations are compiled as specialisations (branch-free inner loop);
+// anything else runs the E_GENERIC instantiation, which tests the same flags at run time.
+constexpr int E_BIAS_N = 1, E_BIAS_M = 2, E_ROWVEC = 4, E_ROWSCALE = 8, E_RESID = 16, E_SILU = 32, E_F32 = 64,
+              E_BF16 = 128, E_STATS = 256, E_ALPHA = 512, E_GENERIC = 1 << 14, E_SOFTMAX = 1 << 15;
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   using L = Smem<BN>;
+  constexpr bool kSoftmax = (EPI & E_SOFTMAX) != 0;
+  constexpr bool kGeneric = (EPI & E_GENERIC) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* sm = smem_raw;
@@ -185,16 +192,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
     float* stg = staging + q * (32 * kStgPitch);
     const int c4 = (lane & 7) * 4;
     const int rsub = lane >> 3;
-    const bool has_bias_n = p.bias != nullptr && !p.bias_along_m;
-    const bool has_bias_m = p.bias != nullptr && p.bias_along_m;
-    const bool has_rowvec = p.rowvec != nullptr;
-    const bool has_rowscale = p.rowscale != nullptr;
-    const bool has_resid = p.resid != nullptr;
-    const bool has_f32 = p.out_f32 != nullptr;
-    const bool has_bf16 = p.out_bf16 != nullptr;
-    const bool do_silu = p.silu != 0;
-    const bool do_stats = p.stats != nullptr;
+    const bool has_bias_n = kGeneric ? (p.bias != nullptr && !p.bias_along_m) : (EPI & E_BIAS_N) != 0;
+    const bool has_bias_m = kGeneric ? (p.bias != nullptr && p.bias_along_m) : (EPI & E_BIAS_M) != 0;
+    const bool has_rowvec = kGeneric ? (p.rowvec != nullptr) : (EPI & E_ROWVEC) != 0;
+    const bool has_rowscale = kGeneric ? (p.rowscale != nullptr) : (EPI & E_ROWSCALE) != 0;
+    const bool has_resid = kGeneric ? (p.resid != nullptr) : (EPI & E_RESID) != 0;
+    const bool has_f32 = kGeneric ? (p.out_f32 != nullptr) : (EPI & E_F32) != 0;
+    const bool has_bf16 = kGeneric ? (p.out_bf16 != nullptr) : (EPI & E_BF16) != 0;
+    const bool do_silu = kGeneric ? (p.silu != 0) : (EPI & E_SILU) != 0;
+    const bool do_stats = kGeneric ? (p.stats != nullptr) : (EPI & E_STATS) != 0;
+    const bool do_alpha = kGeneric ? true : (EPI & E_ALPHA) != 0;
     const float alpha = p.alpha;
+    const int ldc = static_cast<int>(p.ldc);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -257,6 +266,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
         }
         if (row0 + lane < p.M) p.rowsum_out[static_cast<long long>(c.b) * p.M + row0 + lane] = sum;
       } else {
+        // tile-relative bases: everything inside the chunk loop uses 32-bit offsets from these
+        const long long tbase = obase + static_cast<long long>(row0) * ldc + c.nt * BN;
+        float* const outf = has_f32 ? p.out_f32 + tbase : nullptr;
+        __nv_bfloat16* const outb = has_bf16 ? p.out_bf16 + tbase : nullptr;
+        const float* const resp = has_resid ? p.resid + tbase : nullptr;
+        const int rows_valid = p.M - row0;
+        const float* rv_lo = nullptr;
+        const float* rv_hi = nullptr;
+        if (has_rowvec) {
+          // a 32-row block spans one sample (H*W >= 32) or two (H*W == 16: rows 0-15 | 16-31)
+          rv_lo = p.rowvec + static_cast<long long>(row0 >> p.rowvec_shift) * p.rowvec_ld + c.nt * BN;
+          rv_hi = p.rowvec + static_cast<long long>((row0 + 16) >> p.rowvec_shift) * p.rowvec_ld + c.nt * BN;
+        }
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           tmem_ld_32x32b_x32(taddr + ch * 32, r);
@@ -272,63 +294,69 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
-          const int col = c.nt * BN + ch * 32 + c4;
-          const bool colok = col < p.N;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_bias_n && colok) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-          float st[16];  // [half][sum|sumsq][4 cols]
-#pragma unroll
-          for (int i = 0; i < 16; ++i) st[i] = 0.f;
+          const int cc = ch * 32 + c4;  // column inside the tile
+          const bool colok = c.nt * BN + cc < p.N;
+          // per-column additive terms of the two 16-row halves: bias (+ time-embedding projection)
+          float4 add_lo = make_float4(0.f, 0.f, 0.f, 0.f), add_hi = add_lo;
+          if (colok) {
+            if (has_bias_n) add_lo = add_hi = __ldg(reinterpret_cast<const float4*>(p.bias + c.nt * BN + cc));
+            if (has_rowvec) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(rv_lo + cc));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rv_hi + cc));
+              add_lo.x += a.x; add_lo.y += a.y; add_lo.z += a.z; add_lo.w += a.w;
+              add_hi.x += b.x; add_hi.y += b.y; add_hi.z += b.z; add_hi.w += b.w;
+            }
+          }
           // Issue all residual loads of this 32x32 block before any store: `resid` and `out` may alias
           // from the compiler's point of view, which would otherwise serialise one HBM round trip per row.
           float4 rs8[8];
           if (has_resid) {
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) {
-              const int row = row0 + i8 * 4 + rsub;
-              rs8[i8] = (row < p.M && colok)
-                            ? __ldg(reinterpret_cast<const float4*>(p.resid + obase + static_cast<long long>(row) * p.ldc + col))
+              const int rr = i8 * 4 + rsub;
+              rs8[i8] = (rr < rows_valid && colok)
+                            ? __ldg(reinterpret_cast<const float4*>(resp + rr * ldc + cc))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
+          float st[16];  // [half][sum|sumsq][4 cols]
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st[i] = 0.f;
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int rr = i8 * 4 + rsub;
-            const int row = row0 + rr;
             float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgPitch + c4);
-            if (row < p.M && colok) {
+            if (rr < rows_valid && colok) {
               if (has_rowscale) {
-                const float rinv = 1.0f / p.rowscale[static_cast<long long>(c.b) * p.M + row];
+                const float rinv = 1.0f / p.rowscale[static_cast<long long>(c.b) * p.M + row0 + rr];
                 v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv;
               }
-              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+              const float4 ad = i8 < 4 ? add_lo : add_hi;
+              v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
               if (has_bias_m) {
-                const float bm = p.bias[row];
+                const float bm = p.bias[row0 + rr];
                 v.x += bm; v.y += bm; v.z += bm; v.w += bm;
               }
-              if (has_rowvec) {
-                const float4 rv = *reinterpret_cast<const float4*>(
-                    p.rowvec + static_cast<long long>(row >> p.rowvec_shift) * p.rowvec_ld + col);
-                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-              }
               if (do_silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-              const long long o = obase + static_cast<long long>(row) * p.ldc + col;
               if (has_resid) {
                 const float4 rs = rs8[i8];
                 v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
               }
-              v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
-              if (has_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+              if (do_alpha) { v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha; }
+              const int o = rr * ldc + cc;
+              if (has_f32) *reinterpret_cast<float4*>(outf + o) = v;
               if (has_bf16) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
                 uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(p.out_bf16 + o) = pk;
+                *reinterpret_cast<uint2*>(outb + o) = pk;
               }
-              float* h = st + (i8 >= 4 ? 8 : 0);
-              h[0] += v.x; h[1] += v.y; h[2] += v.z; h[3] += v.w;
-              h[4] += v.x * v.x; h[5] += v.y * v.y; h[6] += v.z * v.z; h[7] += v.w * v.w;
+              if (do_stats) {
+                float* h = st + (i8 >= 4 ? 8 : 0);
+                h[0] += v.x; h[1] += v.y; h[2] += v.z; h[3] += v.w;
+                h[4] += v.x * v.x; h[5] += v.y * v.y; h[6] += v.z * v.z; h[7] += v.w * v.w;
+              }
             }
           }
           if (do_stats) {
@@ -389,14 +417,52 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
   }
 }
 
-template <int BN, bool kSoftmax>
+template <int BN, int EPI>
 int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   const int total = p.m_tiles * p.n_tiles * p.batch;
   if (total <= 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
   const size_t smem = Smem<BN>::total(p.num_stages);
-  gemm_kernel<BN, kSoftmax><<<grid, kNumThreads, smem, stream>>>(p);
+  gemm_kernel<BN, EPI><<<grid, kNumThreads, smem, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
+}
+
+// epilogue specialisations (every lowering's common cases); others use E_GENERIC
+#define DP_EPI_LIST(X)                                          \
+  X(E_BIAS_N | E_ROWVEC | E_F32 | E_STATS)                      \
+  X(E_BIAS_N | E_RESID | E_F32 | E_STATS | E_ALPHA)             \
+  X(E_BIAS_N | E_F32 | E_STATS | E_ALPHA)                       \
+  X(E_BIAS_N | E_RESID | E_F32 | E_STATS)                       \
+  X(E_BIAS_N | E_F32 | E_STATS)                                 \
+  X(E_BIAS_N | E_BF16)                                          \
+  X(E_BIAS_N | E_SILU | E_BF16)                                 \
+  X(E_BIAS_N | E_F32)                                           \
+  X(E_BIAS_M | E_BF16)                                          \
+  X(E_ROWSCALE | E_BF16)                                        \
+  X(E_GENERIC)                                                  \
+  X(E_SOFTMAX)
+
+int epi_mask_of(const GemmParams& p) {
+  int m = 0;
+  if (p.bias) m |= p.bias_along_m ? E_BIAS_M : E_BIAS_N;
+  if (p.rowvec) m |= E_ROWVEC;
+  if (p.rowscale) m |= E_ROWSCALE;
+  if (p.resid) m |= E_RESID;
+  if (p.silu) m |= E_SILU;
+  if (p.out_f32) m |= E_F32;
+  if (p.out_bf16) m |= E_BF16;
+  if (p.stats) m |= E_STATS;
+  if (p.alpha != 1.0f) m |= E_ALPHA;
+  return m;
+}
+
+template <int BN>
+int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
+#define X(M) \
+  if (mask == (M)) return launch_t<BN, (M)>(p, num_sms, stream);
+  DP_EPI_LIST(X)
+#undef X
+  return launch_t<BN, E_GENERIC>(p, num_sms, stream);
 }
 
 }  // namespace
@@ -414,15 +480,15 @@ int gemm_max_stages(int bn) {
 
 int gemm_init() {
   cudaError_t e;
-#define DP_SET(BN, SM)                                                                         \
-  e = cudaFuncSetAttribute(gemm_kernel<BN, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                           static_cast<int>(Smem<BN>::total(gemm_max_stages(BN))));            \
+#define X(M)                                                                                       \
+  e = cudaFuncSetAttribute(gemm_kernel<128, (M)>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           static_cast<int>(Smem<128>::total(gemm_max_stages(128))));              \
+  if (e != cudaSuccess) return static_cast<int>(e);                                                \
+  e = cudaFuncSetAttribute(gemm_kernel<256, (M)>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           static_cast<int>(Smem<256>::total(gemm_max_stages(256))));              \
   if (e != cudaSuccess) return static_cast<int>(e);
-  DP_SET(128, false)
-  DP_SET(256, false)
-  DP_SET(128, true)
-  DP_SET(256, true)
-#undef DP_SET
+  DP_EPI_LIST(X)
+#undef X
   return 0;
 }
 
@@ -469,10 +535,8 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn) {
 }
 
 int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream) {
-  if (bn == 256) {
-    return softmax ? launch_t<256, true>(p, num_sms, stream) : launch_t<256, false>(p, num_sms, stream);
-  }
-  return softmax ? launch_t<128, true>(p, num_sms, stream) : launch_t<128, false>(p, num_sms, stream);
+  const int mask = softmax ? E_SOFTMAX : epi_mask_of(p);
+  return bn == 256 ? dispatch<256>(p, mask, num_sms, stream) : dispatch<128>(p, mask, num_sms, stream);
 }
 
 }  // namespace dp
