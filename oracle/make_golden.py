@@ -1,0 +1,100 @@
+"""Generate the committed golden vectors from the REFERENCE's own modules (build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+Needs /root/reference (read-only) and a writable TORCH_EXTENSIONS_DIR: importing score_sde.models.ncsnpp
+JIT-builds the reference's two StyleGAN2 ops (~2-4 min the first time, no GPU needed). Weights come from the
+seeded factory oracle/weights.py; inputs and noise from seeded torch generators, so the GPU box regenerates
+identical operands without the reference.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ncsnpp as O, ref_import, sde as OS, weights  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def inputs(seed, B, S):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    t = torch.rand(B, generator=g) * 0.2 + 0.001
+    return x, t
+
+
+def euler_shim(sde, y0, ts, method="euler", bm=None, dt=1e-3, **kw):
+    """Fixed-step Ito Euler with torchsde's step grid; `bm(ta, tb)` must return the Brownian increment."""
+    assert method == "euler"
+    t, y = ts[0], y0
+    while t < ts[-1]:
+        tn = torch.minimum(t + dt, ts[-1])
+        y = y + sde.f(t, y) * (tn - t) + sde.g(t, y) * bm(t, tn)
+        t = tn
+    return torch.stack([y0, y])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(False)
+    # ---- 1. full CIFAR-10 DDPM++ (configs/cifar10.yml), one UNet evaluation --------------------------------
+    model, cfg = ref_import.build_ncsnpp()
+    sd = weights.make_state_dict(O.param_shapes(O.CIFAR10_CFG), seed=0)
+    missing = model.load_state_dict(sd, strict=False)
+    assert set(missing.missing_keys) <= {"sigmas"} and not missing.unexpected_keys, missing
+    x, t = inputs(100, 2, 32)
+    y = model(x, t * 999)
+    np.savez_compressed(os.path.join(OUT, "ncsnpp_cifar10_eval.npz"), x=x.numpy(), labels=(t * 999).numpy(),
+                        y=y.numpy(), seed=0)
+    print("cifar10 eval: |y| mean", y.abs().mean().item())
+
+    # ---- 2. reduced configurations (same block types) -----------------------------------------------------
+    for name, ov, cfg_o in [
+        ("tinyA", dict(nf=64, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[8], **{"data.image_size": 16}),
+         O.tiny_cfg(64, (1, 2), 1, (8,), 16)),
+        ("tinyB", dict(nf=64, ch_mult=[1, 2, 2], num_res_blocks=1, attn_resolutions=[16], **{"data.image_size": 32}),
+         O.tiny_cfg(64, (1, 2, 2), 1, (16,), 32)),
+    ]:
+        m, c = ref_import.build_ncsnpp(ov)
+        sdt = weights.make_state_dict(O.param_shapes(cfg_o), seed=1)
+        r = m.load_state_dict(sdt, strict=False)
+        assert set(r.missing_keys) <= {"sigmas"} and not r.unexpected_keys, r
+        S = cfg_o.image_size
+        x, t = inputs(200, 3, S)
+        y = m(x, t * 999)
+        # reference RevVPSDE driven by the Euler shim with injected noise (runners/diffpure_sde.py:50-147)
+        ref_import.install(euler_shim)
+        from runners.diffpure_sde import RevVPSDE
+        rev = RevVPSDE(model=m, score_type="score_sde", img_shape=(3, S, S))
+        t_star = 4
+        g = torch.Generator().manual_seed(300)
+        x0 = torch.rand(3, 3, S, S, generator=g) * 2 - 1
+        e0 = torch.randn(3, 3, S, S, generator=g)
+        steps = OS.num_steps(t_star)
+        z = torch.randn(steps, 3, 3, S, S, generator=g)
+        xs = OS.forward_diffuse(x0, e0, t_star)
+        grid = OS.time_grid(t_star)
+        ts = torch.stack([grid[0], grid[-1]])
+        k = {"i": 0}
+
+        def bm(ta, tb):
+            dw = z[k["i"]].reshape(3, -1) * torch.sqrt(tb - ta)
+            k["i"] += 1
+            return dw
+
+        out = euler_shim(rev, xs.reshape(3, -1), ts, bm=bm)[-1].reshape(3, 3, S, S)
+        f0 = rev.f(grid[0], xs.reshape(3, -1)).reshape(3, 3, S, S)
+        g0 = rev.g(grid[0], xs.reshape(3, -1))[:, 0]
+        np.savez_compressed(os.path.join(OUT, f"ncsnpp_{name}.npz"), x=x.numpy(), labels=(t * 999).numpy(),
+                            y=y.numpy(), x0=x0.numpy(), e0=e0.numpy(), z=z.numpy(), t_star=t_star,
+                            loop_out=out.numpy(), f0=f0.numpy(), g0=g0.numpy(), seed=1)
+        print(name, "eval |y|", y.abs().mean().item(), "loop |x|", out.abs().mean().item(), "steps", steps)
+
+
+if __name__ == "__main__":
+    main()
