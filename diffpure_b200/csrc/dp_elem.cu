@@ -92,6 +92,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, int ppc) {
   const int tid = threadIdx.x;
   const int HW = p.H * p.W;
 
+  if (p.stats0 == nullptr) {
+    // identity: plain cast / resample of the raw stream (conv resampling layers)
+    for (int c = tid; c < C; c += blockDim.x) { sc[c] = 1.f; sh[c] = 0.f; }
+    __syncthreads();
+  } else {
   for (int c = tid; c < C; c += blockDim.x) {
     const float* st;
     int P, Cx, cl;
@@ -137,6 +142,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, int ppc) {
   }
   __syncthreads();
 
+  }
   const int Ho = p.resample == 1 ? p.H * 2 : (p.resample == 2 ? p.H / 2 : p.H);
   const int Wo = p.resample == 1 ? p.W * 2 : (p.resample == 2 ? p.W / 2 : p.W);
   const int HWo = Ho * Wo;
@@ -527,6 +533,45 @@ int launch_attn_small(const AttnSmallParams& p, cudaStream_t s) {
                                        static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024));
   if (e != cudaSuccess) return static_cast<int>(e);
   attn_small_kernel<<<dim3(p.heads, p.B), 256, smem, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// row softmax for long sequences (T > 256): one warp per row, fp32 logits -> normalised bf16
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ src,
+                                                           __nv_bfloat16* __restrict__ out, long long rows, int T) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* s4 = reinterpret_cast<const float4*>(src + row * T);
+  const int n4 = T / 4;
+  float mx = -INFINITY;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = __ldg(s4 + i);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int m = 16; m > 0; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  float sum = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = __ldg(s4 + i);
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+  const float inv = 1.0f / sum;
+  uint2* o2 = reinterpret_cast<uint2*>(out + row * T);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = __ldg(s4 + i);
+    uint2 pk;
+    pk.x = pack_bf16x2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
+    pk.y = pack_bf16x2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
+    o2[i] = pk;
+  }
+}
+
+int launch_softmax_rows(const float* src, __nv_bfloat16* out, long long rows, int T, cudaStream_t s) {
+  if (T % 4) return static_cast<int>(cudaErrorInvalidValue);
+  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(src, out, rows, T);
   return static_cast<int>(cudaGetLastError());
 }
 

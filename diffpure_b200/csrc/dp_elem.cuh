@@ -67,6 +67,8 @@ struct AttnSmallParams {
   const __nv_bfloat16* qkv; __nv_bfloat16* out; int B, T, heads, d; float scale;
 };
 int launch_attn_small(const AttnSmallParams& p, cudaStream_t s);
+// fp32 [rows, T] -> softmax over T -> bf16 [rows, T]
+int launch_softmax_rows(const float* src, __nv_bfloat16* out, long long rows, int T, cudaStream_t s);
 
 // x_state[b,h,w,c] = sx * x0[b,c,h,w] + se * noise  (noise: tensor or counter-based normal stream 0)
 int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nhwc, int B, int C, int HW,

@@ -17,7 +17,7 @@ namespace {
 
 std::string g_create_error;
 
-enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL };
+enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL, OP_SOFTMAX };
 
 struct StatsReduce {
   const float* in;
@@ -37,6 +37,7 @@ struct Op {
   dp::ConvInParams cin;
   dp::ConvOutParams cout_;
   dp::AttnSmallParams attn;
+  dp_softmax_desc smax;
 };
 
 }  // namespace
@@ -150,6 +151,10 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
     }
     case OP_ATTN_SMALL:
       rc = dp::launch_attn_small(op.attn, s);
+      break;
+    case OP_SOFTMAX:
+      rc = dp::launch_softmax_rows(op.smax.src, static_cast<__nv_bfloat16*>(op.smax.out_bf16), op.smax.rows,
+                                   op.smax.T, s);
       break;
   }
   if (rc != 0)
@@ -352,9 +357,12 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     if (a.stride != 1 && a.stride != 2) return fail(e, DP_ERR_INVALID, "gemm: stride must be 1 or 2");
     const int win = d->W * a.stride, hin = d->H * a.stride;
     // plain / batched GEMM: the map spans all batch entries' rows
-    const int wdim = (d->H == 1) ? (p.batch > 1 ? (p.batch - 1) * d->a_batch_rows + d->W : d->W) : win;
-    if (dp::make_act_tmap(&p.a[s].tmap, a.act_bf16, a.C, a.c_total, wdim, hin, d->B, tb.bw, tb.bh, tb.bn, a.stride,
-                          &err))
+    const int inner_n = d->inner > 0 ? d->inner : 1;
+    const int outer_n = p.batch / inner_n;
+    const int wdim = (d->H == 1) ? ((outer_n - 1) * d->a_batch_rows + (inner_n - 1) * d->a_inner_rows + d->W) : win;
+    // the map exposes the whole channel pitch so per-head channel offsets stay in bounds
+    if (dp::make_act_tmap(&p.a[s].tmap, a.act_bf16, a.c_total, a.c_total, wdim, hin, d->B, tb.bw, tb.bh, tb.bn,
+                          a.stride, &err))
       return fail(e, DP_ERR_CUDA, "gemm: A tensor map: " + err);
     p.a[s].taps = a.taps;
     p.a[s].kchunks = a.C / 64;
@@ -363,11 +371,18 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     ktotal += static_cast<long long>(a.taps) * a.C;
   }
   p.nseg = d->nseg;
-  if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, ktotal, d->w_rows, d->w_pitch, bn, &err))
+  if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, d->w_cols > 0 ? d->w_cols : ktotal, d->w_rows, d->w_pitch, bn, &err))
     return fail(e, DP_ERR_CUDA, "gemm: B tensor map: " + err);
   p.a_batch_rows = d->a_batch_rows;
   p.b_batch_rows = d->b_batch_rows;
   p.out_batch_stride = d->out_batch_stride;
+  p.inner = d->inner > 0 ? d->inner : 1;
+  p.a_inner_k = d->a_inner_k;
+  p.a_inner_rows = d->a_inner_rows;
+  p.b_inner_k = d->b_inner_k;
+  p.b_inner_rows = d->b_inner_rows;
+  p.out_inner_stride = d->out_inner_stride;
+  if (p.batch % p.inner) return fail(e, DP_ERR_INVALID, "gemm: batch must be a multiple of inner");
   p.bias = d->bias;
   p.bias_along_m = d->bias_along_m;
   p.rowvec = d->rowvec;
@@ -396,7 +411,7 @@ int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d) {
   if (!e || !d) return DP_ERR_INVALID;
   if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
   const int C = d->C0 + d->C1;
-  if (d->C0 % 8 || d->C1 % 8 || C % d->groups) return fail(e, DP_ERR_INVALID, "gn: channel counts");
+  if (d->C0 % 8 || d->C1 % 8 || (d->stats0 && C % d->groups)) return fail(e, DP_ERR_INVALID, "gn: channel counts");
   dp::GnParams p;
   std::memset(&p, 0, sizeof(p));
   p.src0 = d->src0; p.stats0 = d->stats0; p.C0 = d->C0; p.P0 = d->P0;
@@ -487,6 +502,17 @@ int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d) {
   op.attn.qkv = static_cast<const __nv_bfloat16*>(d->qkv_bf16);
   op.attn.out = static_cast<__nv_bfloat16*>(d->out_bf16);
   op.attn.B = d->B; op.attn.T = d->T; op.attn.heads = d->heads; op.attn.d = d->d; op.attn.scale = d->scale;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->T % 4) return fail(e, DP_ERR_INVALID, "softmax_rows: T must be a multiple of 4");
+  Op op;
+  op.kind = OP_SOFTMAX;
+  op.smax = *d;
   e->ops.push_back(op);
   return DP_OK;
 }

@@ -37,6 +37,7 @@ struct Smem {
 
 struct Tile {
   int b, mt, nt, n0, h0, w0;
+  int bo, hd;  // outer batch entry, head
 };
 
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
@@ -45,6 +46,8 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
   const int r = t / p.n_tiles;
   c.mt = r % p.m_tiles;
   c.b = r / p.m_tiles;
+  c.bo = c.b / p.inner;
+  c.hd = c.b - c.bo * p.inner;
   if (p.imgs_per_tile > 1) {
     c.n0 = c.mt * p.imgs_per_tile;
     c.h0 = 0;
@@ -126,20 +129,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const Tile c = decode_tile(p, t);
         int kglobal = 0;
-        const int brow = c.nt * BN + c.b * p.b_batch_rows;
+        const int brow = c.nt * BN + c.bo * p.b_batch_rows + c.hd * p.b_inner_rows;
+        const int a_k0 = c.hd * p.a_inner_k;
+        const int b_k0 = c.hd * p.b_inner_k;
         for (int s = 0; s < p.nseg; ++s) {
           const GemmASeg& seg = p.a[s];
           for (int tap = 0; tap < seg.taps; ++tap) {
             const int ky = (seg.taps == 9) ? tap / 3 : 0;
             const int kx = (seg.taps == 9) ? tap - 3 * ky : 0;
-            const int c1 = c.w0 * seg.stride + kx - seg.pad + c.b * p.a_batch_rows;
+            const int c1 = c.w0 * seg.stride + kx - seg.pad + c.bo * p.a_batch_rows + c.hd * p.a_inner_rows;
             const int c2 = c.h0 * seg.stride + ky - seg.pad;
             for (int kc = 0; kc < seg.kchunks; ++kc) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
               const uint32_t sa = base + stage * L::kStageBytes;
-              tma_load_4d(sa, &seg.tmap, full_bar(stage), kc * kBlockK, c1, c2, c.n0);
-              tma_load_2d(sa + kStageABytes, &p.tmap_b, full_bar(stage), kglobal, brow);
+              tma_load_4d(sa, &seg.tmap, full_bar(stage), a_k0 + kc * kBlockK, c1, c2, c.n0);
+              tma_load_2d(sa + kStageABytes, &p.tmap_b, full_bar(stage), b_k0 + kglobal, brow);
               kglobal += kBlockK;
               if (++stage == stages) {
                 stage = 0;
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       const int row0 = c.mt * kBlockM + q * 32;  // row within the batch entry
-      const long long obase = static_cast<long long>(c.b) * p.out_batch_stride;
+      const long long obase = static_cast<long long>(c.bo) * p.out_batch_stride +
+                              static_cast<long long>(c.hd) * p.out_inner_stride;
       uint32_t r[32];
 
       if constexpr (kSoftmax) {
@@ -531,6 +537,7 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn) {
   p.N = N;
   p.n_tiles = (N + bn - 1) / bn;
   if (p.batch <= 0) p.batch = 1;
+  if (p.inner <= 0) p.inner = 1;
   p.num_stages = gemm_max_stages(bn);
 }
 

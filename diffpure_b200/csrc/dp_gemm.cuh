@@ -42,8 +42,15 @@ struct GemmParams {
   int M;                       // valid rows per batch entry
   int N;                       // valid columns
   int m_tiles, n_tiles, batch;
-  int a_batch_rows;  // added to the W coordinate of A per batch entry (batched GEMM)
-  int b_batch_rows;  // added to the row coordinate of B per batch entry
+  int a_batch_rows;  // added to the W coordinate of A per (outer) batch entry (batched GEMM)
+  int b_batch_rows;  // added to the row coordinate of B per (outer) batch entry
+  // two-level batch (attention heads): batch index = outer * inner + head
+  int inner;             // heads per outer entry (>= 1)
+  int a_inner_k;         // A channel-coordinate offset per head
+  int a_inner_rows;      // A row (W coordinate) offset per head
+  int b_inner_k;         // B K-coordinate offset per head
+  int b_inner_rows;      // B row offset per head
+  long long out_inner_stride;  // output element offset per head
   int num_stages;
   // ---- epilogue ----
   const float* bias;  // [N] (or [M] if bias_along_m)

@@ -131,6 +131,10 @@ class Engine:
                     d.a[i] = _lib.GemmASeg(self._p(seg.act), seg.C, seg.c_total, seg.taps, seg.stride, seg.pad)
                 d.nseg = len(a["a"])
                 d.w_bf16 = self._p(a["w"]); d.w_rows = a["w_rows"]; d.w_pitch = a["w_pitch"]
+                d.w_cols = a["w_cols"]
+                d.inner, d.a_inner_k, d.b_inner_k = a["inner"], a["a_inner_k"], a["b_inner_k"]
+                d.a_inner_rows = a["a_inner_rows"]
+                d.b_inner_rows, d.out_inner_stride = a["b_inner_rows"], a["out_inner_stride"]
                 d.B, d.H, d.W, d.N = a["B"], a["H"], a["W"], a["N"]
                 d.batch, d.a_batch_rows, d.b_batch_rows = a["batch"], a["a_batch_rows"], a["b_batch_rows"]
                 d.out_batch_stride = a["out_batch_stride"]
@@ -162,6 +166,9 @@ class Engine:
                 d = _lib.AttnSmallDesc(self._p(a["qkv"]), self._p(a["out"]), a["B"], a["T"], a["heads"], a["d"],
                                        a["scale"])
                 self._check(L.dp_op_attn_small(self.h, C.byref(d)), "dp_op_attn_small")
+            elif op.kind == "softmax_rows":
+                d = _lib.SoftmaxDesc(self._p(a["src"]), self._p(a["out"]), a["rows"], a["T"])
+                self._check(L.dp_op_softmax_rows(self.h, C.byref(d)), "dp_op_softmax_rows")
             else:
                 raise ValueError(f"unknown op kind {op.kind}")
 
@@ -212,7 +219,8 @@ class Engine:
         self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), None), "dp_purify")
         return out
 
-    OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "conv_out", "attn_small")
+    OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "conv_out", "attn_small",
+                "softmax_rows")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

@@ -22,9 +22,11 @@ class GemmASeg(C.Structure):
 
 class GemmDesc(C.Structure):
     _fields_ = [("a", GemmASeg * 2), ("nseg", C.c_int), ("w_bf16", C.c_void_p), ("w_rows", C.c_longlong),
-                ("w_pitch", C.c_longlong), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("N", C.c_int),
-                ("batch", C.c_int), ("a_batch_rows", C.c_int), ("b_batch_rows", C.c_int),
-                ("out_batch_stride", C.c_longlong), ("bias", C.c_void_p), ("bias_along_m", C.c_int),
+                ("w_pitch", C.c_longlong), ("w_cols", C.c_longlong), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("N", C.c_int), ("batch", C.c_int), ("a_batch_rows", C.c_int), ("b_batch_rows", C.c_int),
+                ("out_batch_stride", C.c_longlong), ("inner", C.c_int), ("a_inner_k", C.c_int), ("a_inner_rows", C.c_int),
+                ("b_inner_k", C.c_int), ("b_inner_rows", C.c_int), ("out_inner_stride", C.c_longlong),
+                ("bias", C.c_void_p), ("bias_along_m", C.c_int),
                 ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int), ("rowvec_rows_per_sample", C.c_int),
                 ("rowscale", C.c_void_p), ("resid", C.c_void_p), ("alpha", C.c_float), ("silu", C.c_int),
                 ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("ldc", C.c_longlong), ("stats", C.c_void_p),
@@ -59,6 +61,10 @@ class AttnSmallDesc(C.Structure):
                 ("heads", C.c_int), ("d", C.c_int), ("scale", C.c_float)]
 
 
+class SoftmaxDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("out_bf16", C.c_void_p), ("rows", C.c_longlong), ("T", C.c_int)]
+
+
 class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
@@ -85,6 +91,7 @@ SYMBOLS = {
     "dp_op_conv_in": (C.c_int, [C.c_void_p, C.POINTER(ConvInDesc)]),
     "dp_op_conv_out": (C.c_int, [C.c_void_p, C.POINTER(ConvOutDesc)]),
     "dp_op_attn_small": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallDesc)]),
+    "dp_op_softmax_rows": (C.c_int, [C.c_void_p, C.POINTER(SoftmaxDesc)]),
     "dp_program_size": (C.c_int, [C.c_void_p]),
     "dp_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "dp_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

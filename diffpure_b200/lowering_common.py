@@ -65,3 +65,49 @@ def new_act(prog: Program, name, B, C, H, W, with_stats=True):
 def act_seg(t, C, taps=1, stride=1, c_total=None, offset=0):
     from .program import view
     return ASeg(view(t, offset), C, C if c_total is None else c_total, taps, stride, 1 if (taps == 9 and stride == 1) else 0)
+
+
+def lower_attention(prog, name, hn, wq, wk, wv, bq, bk, bv, B, T, C, heads, scale):
+    """Self-attention core on a normalised bf16 input hn [B*T, C]: returns o bf16 [B*T, C] with channel h*d + c.
+
+    wq/wk/wv: [C, C] (out, in) with output rows ordered head-major; b*: [C].
+      T <= 64        : one GEMM for q|k|v, then the whole-sequence smem kernel
+      T in {128,256} : q|k GEMM, V^T GEMM (weights as A operand), tcgen05 S GEMM with the softmax epilogue
+                       (numerator + row sums), tcgen05 O GEMM scaled by 1/rowsum
+      longer T       : fp32 logits to HBM, row-softmax kernel, O GEMM
+    """
+    from .program import view
+    d = C // heads
+    o = prog.tensor(name + ".o", B * T * C, "bf16")
+    if T <= 64:
+        qkv = prog.tensor(name + ".qkv", B * T * 3 * C, "bf16")
+        prog.gemm([act_seg(hn, C)], prog.const_bf16(name + ".wqkv", torch.cat([wq, wk, wv], 0)), 3 * C, C, 1, 1, B * T,
+                  3 * C, bias=prog.const_f32(name + ".bqkv", torch.cat([bq, bk, bv])), out_bf16=qkv)
+        prog.attn_small(qkv, o, B, T, heads, d, scale)
+        return o
+    assert T % 128 == 0 and d % 64 == 0, "tensor-core attention needs T % 128 == 0 and head dim % 64 == 0"
+    qk = prog.tensor(name + ".qk", B * T * 2 * C, "bf16")
+    prog.gemm([act_seg(hn, C)], prog.const_bf16(name + ".wqk", torch.cat([wq, wk], 0)), 2 * C, C, 1, 1, B * T, 2 * C,
+              bias=prog.const_f32(name + ".bqk", torch.cat([bq, bk])), out_bf16=qk)
+    # V^T per sample (all heads stacked): [C, T] = Wv[C, C] . hn_b[T, C]^T  (weights as the A operand, bias along M)
+    vt = prog.tensor(name + ".vt", B * C * T, "bf16")
+    prog.gemm([act_seg(prog.const_bf16(name + ".wv", wv), C)], hn, B * T, C, 1, 1, C, T, batch=B, a_batch_rows=0,
+              b_batch_rows=T, out_batch_stride=C * T, bias=prog.const_f32(name + ".bv", bv), bias_along_m=1,
+              out_bf16=vt, ldc=T)
+    pm = prog.tensor(name + ".p", B * heads * T * T, "bf16")
+    s_args = dict(batch=B * heads, inner=heads, a_batch_rows=T, a_inner_k=d, b_batch_rows=T, b_inner_k=d, w_cols=C,
+                  out_batch_stride=heads * T * T, out_inner_stride=T * T, ldc=T)
+    a_q = [act_seg(qk, d, c_total=2 * C)]
+    if T <= 256:
+        rs = prog.tensor(name + ".rowsum", B * heads * T, "f32")
+        prog.gemm(a_q, view(qk, C), B * T, 2 * C, 1, 1, T, T, out_bf16=pm, softmax=1, softmax_scale=scale,
+                  rowsum_out=rs, **s_args)
+    else:
+        rs = None
+        logits = prog.tensor(name + ".s", B * heads * T * T, "f32")
+        prog.gemm(a_q, view(qk, C), B * T, 2 * C, 1, 1, T, T, out_f32=logits, alpha=scale, **s_args)
+        prog.softmax_rows(logits, pm, B * heads * T, T)
+    prog.gemm([act_seg(pm, T)], vt, B * C, T, 1, 1, T, d, batch=B * heads, inner=heads, a_batch_rows=heads * T,
+              a_inner_rows=T, b_batch_rows=C, b_inner_rows=d, out_batch_stride=T * C, out_inner_stride=d, rowscale=rs,
+              out_bf16=o, ldc=C)
+    return o

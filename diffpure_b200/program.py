@@ -81,16 +81,27 @@ class Program:
         self.add("embed", out=view(out), B=B, dim=dim, cos_first=cos_first, half_minus_1=half_minus_1)
 
     def gemm(self, a: List[ASeg], w, w_rows, w_pitch, B, H, W, N, *, batch=1, a_batch_rows=0, b_batch_rows=0,
-             out_batch_stride=0, bias=None, bias_along_m=0, rowvec=None, rowvec_ld=0, rowvec_rows_per_sample=1,
+             out_batch_stride=0, inner=1, a_inner_k=0, a_inner_rows=0, b_inner_k=0, b_inner_rows=0, out_inner_stride=0, w_cols=0,
+             bias=None, bias_along_m=0, rowvec=None, rowvec_ld=0, rowvec_rows_per_sample=1,
              rowscale=None, resid=None, alpha=1.0, silu=0, out_f32=None, out_bf16=None, ldc=None, stats=None,
              softmax=0, softmax_scale=1.0, rowsum_out=None):
         self.add("gemm", a=a, w=view(w), w_rows=w_rows, w_pitch=w_pitch, B=B, H=H, W=W, N=N, batch=batch,
                  a_batch_rows=a_batch_rows, b_batch_rows=b_batch_rows, out_batch_stride=out_batch_stride,
-                 bias=view(bias), bias_along_m=bias_along_m, rowvec=view(rowvec), rowvec_ld=rowvec_ld,
+                 inner=inner, a_inner_k=a_inner_k, a_inner_rows=a_inner_rows, b_inner_k=b_inner_k, b_inner_rows=b_inner_rows,
+                 out_inner_stride=out_inner_stride, w_cols=w_cols, bias=view(bias), bias_along_m=bias_along_m, rowvec=view(rowvec), rowvec_ld=rowvec_ld,
                  rowvec_rows_per_sample=rowvec_rows_per_sample, rowscale=view(rowscale), resid=view(resid),
                  alpha=float(alpha), silu=silu, out_f32=view(out_f32), out_bf16=view(out_bf16),
                  ldc=N if ldc is None else ldc, stats=view(stats), softmax=softmax,
                  softmax_scale=float(softmax_scale), rowsum_out=view(rowsum_out))
+
+    def cast(self, *, src, C, B, H, W, out_bf16, resample=0):
+        """Identity gn_apply: bf16 copy (optionally resampled) of a raw fp32 stream tensor."""
+        self.add("gn_apply", src0=view(src), stats0=None, C0=C, P0=0, src1=None, stats1=None, C1=0, P1=0, gamma=None,
+                 beta=None, film=None, film_ld=0, B=B, H=H, W=W, groups=1, eps=0.0, silu=0, resample=resample,
+                 out_bf16=view(out_bf16), raw_bf16=None, raw_f32=None)
+
+    def softmax_rows(self, src, out, rows, T):
+        self.add("softmax_rows", src=view(src), out=view(out), rows=rows, T=T)
 
     def gn_apply(self, *, src0, stats0, C0, P0, gamma, beta, B, H, W, groups, eps, silu, out_bf16, src1=None,
                  stats1=None, C1=0, P1=0, film=None, film_ld=0, resample=0, raw_bf16=None, raw_f32=None):

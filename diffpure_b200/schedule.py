@@ -48,3 +48,71 @@ def vpsde_forward_scales(t_level):
     betas = torch.linspace(BETA_MIN / N_SCALES, BETA_MAX / N_SCALES, N_SCALES).float()
     a = (1 - betas).cumprod(dim=0)
     return float(a[t_level - 1].sqrt()), float((1.0 - a[t_level - 1]).sqrt())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DDPM ancestral chains
+# ---------------------------------------------------------------------------------------------------------
+def _linear_betas64(n, beta_start=None, beta_end=None):
+    if beta_start is None:                                     # guided_diffusion get_named_beta_schedule('linear')
+        scale = 1000 / n
+        beta_start, beta_end = scale * 0.0001, scale * 0.02
+    return np.linspace(beta_start, beta_end, n, dtype=np.float64)
+
+
+def guided_tables(t_levels, n=1000):
+    """Learned-range p_sample of guided_diffusion for timesteps t_levels-1 ... 0
+    (runners/diffpure_guided.py:59-75; gaussian_diffusion.py:119-180,240-334,403-447; respace.py:71-99 with
+    timestep_respacing '1000', i.e. betas re-derived from the cumulative products; rescale_timesteps -> float t).
+    coef row: [sqrt(1/ac), sqrt(1/ac - 1), post_mean_coef1, post_mean_coef2, log beta, post_logvar_clipped, t != 0, 0]."""
+    base = _linear_betas64(n)
+    ac_base = np.cumprod(1.0 - base, axis=0)
+    betas, last = [], 1.0
+    for a in ac_base:                                          # SpacedDiffusion.__init__, respace.py:76-84
+        betas.append(1 - a / last)
+        last = a
+    betas = np.array(betas, dtype=np.float64)
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
+    post_logvar = np.log(np.append(post_var[1], post_var[1:]))
+    c1 = betas * np.sqrt(ac_prev) / (1.0 - ac)
+    c2 = (1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac)
+    idx = np.arange(t_levels - 1, -1, -1)
+    coef = np.stack([np.sqrt(1.0 / ac)[idx], np.sqrt(1.0 / ac - 1)[idx], c1[idx], c2[idx], np.log(betas)[idx],
+                     post_logvar[idx], (idx != 0).astype(np.float64), np.zeros(len(idx))], 1).astype(np.float32)
+    cond = idx.astype(np.float32) * np.float32(1000.0 / n)     # _WrappedModel, respace.py:131-136
+    # forward diffusion uses the fp32 copy of the betas (diffpure_guided.py:39,61-62)
+    a32 = (1 - torch.from_numpy(betas).float()).cumprod(dim=0)
+    return cond, coef, float(a32[t_levels - 1].sqrt()), float((1.0 - a32[t_levels - 1]).sqrt())
+
+
+def ddpm_tables(t_levels, beta_start=0.0001, beta_end=0.02, n=1000, var_type="fixedsmall"):
+    """Fixed-variance DDPM step of the CelebA-HQ runner for timesteps t_levels-1 ... 0
+    (runners/diffpure_ddpm.py:19-23,37-54,80-97,116-129): x <- c0 x + c1 eps + c2 z with
+    c0 = 1/sqrt(alpha_t), c1 = -c0 beta_t/sqrt(1-ac_t) (fp32 tables), c2 = [t != 0] exp(logvar_t / 2)."""
+    betas64 = np.linspace(beta_start, beta_end, n, dtype=np.float64)
+    alphas64 = 1.0 - betas64
+    ac64 = np.cumprod(alphas64, axis=0)
+    ac_prev = np.append(1.0, ac64[:-1])
+    post_var = betas64 * (1.0 - ac_prev) / (1.0 - ac64)
+    if var_type == "fixedlarge":
+        logvar = np.log(np.append(post_var[1], betas64[1:]))
+    elif var_type == "fixedsmall":
+        logvar = np.log(np.maximum(post_var, 1e-20))
+    else:
+        raise ValueError(var_type)
+    betas = torch.from_numpy(betas64).float()                  # L85: fp32 betas drive the step arithmetic
+    alphas = 1.0 - betas
+    ac = alphas.cumprod(dim=0)
+    wscore = betas / torch.sqrt(1 - ac)
+    inv = 1 / torch.sqrt(alphas)
+    idx = np.arange(t_levels - 1, -1, -1)
+    tidx = torch.from_numpy(idx.copy())
+    c0 = inv[tidx]
+    c1 = -(inv[tidx] * wscore[tidx])
+    c2 = torch.exp(0.5 * torch.tensor(logvar, dtype=torch.float)[tidx]) * torch.from_numpy((idx != 0).astype(np.float32))
+    coef = torch.stack([c0, c1, c2], 1).numpy().astype(np.float32)
+    cond = idx.astype(np.float32)
+    return cond, coef, float(ac[t_levels - 1].sqrt()), float((1.0 - ac[t_levels - 1]).sqrt())

@@ -83,11 +83,15 @@ typedef struct {
   const void* w_bf16;   /* [rows, Ktotal] bf16, K contiguous: Ktotal = sum taps*C over segments */
   long long w_rows;     /* rows of the weight/B matrix visible to the map */
   long long w_pitch;    /* elements between rows */
+  long long w_cols;     /* K columns visible to the map (0 = Ktotal) */
   int B, H, W;          /* output grid (plain GEMM: B = 1, H = 1, W = rows) */
   int N;                /* output columns (multiple of 8) */
   int batch;            /* batched GEMM count (attention), else 1 */
   int a_batch_rows, b_batch_rows;
   long long out_batch_stride;
+  int inner;            /* heads per batch entry (two-level batch: index = entry*inner + head), 0/1 = none */
+  int a_inner_k, a_inner_rows, b_inner_k, b_inner_rows; /* per-head offsets: A channel, A row, B K column, B row */
+  long long out_inner_stride;
   const float* bias; int bias_along_m;
   const float* rowvec; int rowvec_ld; int rowvec_rows_per_sample; /* per-sample additive vector */
   const float* rowscale; /* out *= 1/rowscale[b*M + row] */
@@ -99,7 +103,8 @@ typedef struct {
 } dp_gemm_desc;
 
 typedef struct {
-  const float* src0; const float* stats0; int C0; int P0; /* fp32 NHWC + [B][P0][C0][2] partials */
+  const float* src0; const float* stats0; int C0; int P0; /* fp32 NHWC + [B][P0][C0][2] partials;
+                                                             stats0 == NULL: identity (cast / resample only) */
   const float* src1; const float* stats1; int C1; int P1; /* optional channel-concat second source */
   const float* gamma; const float* beta;                  /* [C0+C1] */
   const float* film; int film_ld;                         /* optional [B, film_ld]: scale = [:C], shift = [C:2C] */
@@ -111,6 +116,11 @@ typedef struct {
   void* raw_bf16;         /* optional: resampled raw input as bf16 (1x1 shortcut operand) */
   float* raw_f32;         /* optional: resampled raw input as fp32 (identity residual after resample) */
 } dp_gn_desc;
+
+/* Row softmax of fp32 logits [rows, T] -> normalised bf16 probabilities (long-sequence attention, T > 256). */
+typedef struct {
+  const float* src; void* out_bf16; long long rows; int T;
+} dp_softmax_desc;
 
 typedef struct {
   const float* src; int B, HW, C; /* fp32 [B, HW, C] */
@@ -146,6 +156,7 @@ int dp_op_stats(dp_engine* e, const dp_stats_desc* d);
 int dp_op_conv_in(dp_engine* e, const dp_conv_in_desc* d);
 int dp_op_conv_out(dp_engine* e, const dp_conv_out_desc* d);
 int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d);
+int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d);
 int dp_program_size(const dp_engine* e);
 
 /* Freeze the program for images of [B, C=3, H, W]; captures the CUDA graphs. */
@@ -180,7 +191,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
- * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,
+ * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,8 softmax_rows,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

@@ -96,5 +96,76 @@ def main():
         print(name, "eval |y|", y.abs().mean().item(), "loop |x|", out.abs().mean().item(), "steps", steps)
 
 
+
+
+def golden_adm_and_celeba():
+    """ADM (guided_diffusion) and CelebA-HQ DDPM: reference UNet evaluations and the reference's own reverse steps."""
+    from oracle import adm as A, ddpm_unet as D, ddpm_loops as OL
+    torch.set_grad_enabled(False)
+    # ---- ADM, reduced width/size, all three attention regimes (T = 1024, 256, 64) ------------------------
+    m, diffusion, mc = ref_import.build_adm(num_channels=64, image_size=64, num_res_blocks=1)
+    oc = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    sd = weights.make_state_dict(A.param_shapes(oc), seed=5)
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(400)
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    t = torch.tensor([7, 130])
+    y = m(x, t)
+    m16, _, _ = ref_import.build_adm(num_channels=64, image_size=64, num_res_blocks=1, use_fp16=True)
+    m16.load_state_dict(sd)
+    m16.convert_to_fp16()
+    y16 = m16(x, t)
+    # reference p_sample chain (runners/diffpure_guided.py:59-75), t = 3, noise replayed from the torch RNG stream
+    t_levels = 3
+    x0 = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    betas = torch.from_numpy(diffusion.betas).float()
+    torch.manual_seed(77)
+    e = torch.randn_like(x0)
+    a = (1 - betas).cumprod(dim=0)
+    xx = x0 * a[t_levels - 1].sqrt() + e * (1.0 - a[t_levels - 1]).sqrt()
+    for i in reversed(range(t_levels)):
+        xx = diffusion.p_sample(m, xx, torch.tensor([i] * 2), clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                model_kwargs=None)["sample"]
+    torch.manual_seed(77)
+    e2 = torch.randn_like(x0)
+    z = torch.stack([torch.randn_like(x0) for _ in range(t_levels)])
+    assert torch.equal(e, e2)
+    np.savez_compressed(os.path.join(OUT, "adm_tiny.npz"), x=x.numpy(), t=t.numpy(), y=y.numpy(), y_fp16=y16.numpy(),
+                        x0=x0.numpy(), e0=e.numpy(), z=z.numpy(), t_levels=t_levels, loop_out=xx.numpy(), seed=5)
+    print("adm tiny |y|", y.abs().mean().item(), "fp16-torso rel", ((y16 - y).norm() / y.norm()).item())
+
+    # ---- CelebA-HQ DDPM, reduced ------------------------------------------------------------------------------
+    m, cfg = ref_import.build_celeba({"ch": 64, "ch_mult": [1, 2, 2], "num_res_blocks": 1, "attn_resolutions": [16],
+                                      "data.image_size": 32})
+    oc = D.tiny_cfg(32, 64, (1, 2, 2), 1, (16,))
+    sd = weights.make_state_dict(D.param_shapes(oc), seed=4)
+    m.load_state_dict(sd)
+    x = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    t = torch.tensor([5, 400])
+    y = m(x, t)
+    from runners.diffpure_ddpm import image_editing_denoising_step_flexible_mask, get_beta_schedule
+    betas64 = get_beta_schedule(beta_start=1e-4, beta_end=2e-2, num_diffusion_timesteps=1000)
+    ac = np.cumprod(1.0 - betas64)
+    logvar = np.log(np.maximum(betas64 * (1.0 - np.append(1.0, ac[:-1])) / (1.0 - ac), 1e-20))
+    betas = torch.from_numpy(betas64).float()
+    t_levels = 4
+    x0 = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    torch.manual_seed(78)
+    e = torch.randn_like(x0)
+    a = (1 - betas).cumprod(dim=0)
+    xx = x0 * a[t_levels - 1].sqrt() + e * (1.0 - a[t_levels - 1]).sqrt()
+    for i in reversed(range(t_levels)):
+        xx = image_editing_denoising_step_flexible_mask(xx, t=torch.tensor([i] * 2), model=m, logvar=logvar, betas=betas)
+    torch.manual_seed(78)
+    e2 = torch.randn_like(x0)
+    z = torch.stack([torch.randn_like(x0) for _ in range(t_levels)])
+    np.savez_compressed(os.path.join(OUT, "celeba_tiny.npz"), x=x.numpy(), t=t.numpy(), y=y.numpy(), x0=x0.numpy(),
+                        e0=e.numpy(), z=z.numpy(), t_levels=t_levels, loop_out=xx.numpy(), seed=4)
+    print("celeba tiny |y|", y.abs().mean().item())
+
+
 if __name__ == "__main__":
-    main()
+    if "--adm-celeba" not in sys.argv:
+        main()
+    if "--ncsnpp" not in sys.argv:
+        golden_adm_and_celeba()

@@ -77,3 +77,30 @@ def build_ncsnpp(overrides=None):
     cfg.device = torch.device("cpu")
     model = mutils.create_model(cfg)
     return model.eval(), cfg
+
+
+def build_adm(num_channels=256, image_size=256, num_res_blocks=2, attention_resolutions="32,16,8", use_fp16=False):
+    """Reference ADM UNet (guided_diffusion/unet.py via script_util.create_model_and_diffusion) on CPU."""
+    install()
+    from guided_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    cfg = load_config("imagenet.yml")
+    mc = model_and_diffusion_defaults()
+    mc.update(vars(cfg.model))
+    mc.update(num_channels=num_channels, image_size=image_size, num_res_blocks=num_res_blocks,
+              attention_resolutions=attention_resolutions, use_fp16=use_fp16)
+    model, diffusion = create_model_and_diffusion(**mc)
+    if use_fp16:
+        model.convert_to_fp16()
+    return model.eval(), diffusion, mc
+
+
+def build_celeba(overrides=None):
+    """Reference CelebA-HQ DDPM UNet (ddpm/unet_ddpm.py) on CPU."""
+    install()
+    from ddpm.unet_ddpm import Model
+    cfg = load_config("celeba.yml")
+    if overrides:
+        for k, v in overrides.items():
+            tgt, key = (cfg.data, k[5:]) if k.startswith("data.") else (cfg.model, k)
+            setattr(tgt, key, v)
+    return Model(cfg).eval(), cfg

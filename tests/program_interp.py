@@ -65,11 +65,10 @@ class Interp:
         e = torch.cat([torch.cos(arg), torch.sin(arg)] if cos_first else [torch.sin(arg), torch.cos(arg)], 1)
         self.wr(out, e, (B, dim), (dim, 1))
 
-    def _a_matrix(self, seg, B, H, W, b, a_batch_rows):
+    def _a_matrix(self, seg, B, H, W, b, a_batch_rows, k_off=0):
         if H == 1 and seg.taps == 1:  # plain GEMM rows
-            x = self.rd(seg.act, (W, seg.C), (seg.c_total, 1))
             buf, off = self.flat(seg.act)
-            return torch.as_strided(buf, (W, seg.C), (seg.c_total, 1), off + b * a_batch_rows * seg.c_total)
+            return torch.as_strided(buf, (W, seg.C), (seg.c_total, 1), off + b * a_batch_rows * seg.c_total + k_off)
         s = seg.stride
         Hin, Win = H * s, W * s
         x = self.rd(seg.act, (B, Hin, Win, seg.C), (Hin * Win * seg.c_total, Win * seg.c_total, seg.c_total, 1))
@@ -92,30 +91,34 @@ class Interp:
                 cols.append(patch.reshape(B * H * W, seg.C))
         return torch.cat(cols, 1)
 
-    def op_gemm(self, a, w, w_rows, w_pitch, B, H, W, N, batch, a_batch_rows, b_batch_rows, out_batch_stride, bias,
+    def op_gemm(self, a, w, w_rows, w_pitch, B, H, W, N, batch, a_batch_rows, b_batch_rows, out_batch_stride, inner,
+                a_inner_k, a_inner_rows, b_inner_k, b_inner_rows, out_inner_stride, w_cols, bias,
                 bias_along_m, rowvec, rowvec_ld, rowvec_rows_per_sample, rowscale, resid, alpha, silu, out_f32,
                 out_bf16, ldc, stats, softmax, softmax_scale, rowsum_out):
         M = B * H * W
         ktot = sum(s.taps * s.C for s in a)
-        for b in range(batch):
-            A = torch.cat([self._a_matrix(s, B, H, W, b, a_batch_rows) for s in a], 1)
+        for bi in range(batch):
+            b, hd = bi // inner, bi % inner
+            obs = b * out_batch_stride + hd * out_inner_stride
+            A = torch.cat([self._a_matrix(s, B, H, W, b, a_batch_rows, hd * a_inner_k + hd * a_inner_rows * s.c_total)
+                           for s in a], 1)
             wbuf, woff = self.flat(w)
-            Wt = torch.as_strided(wbuf, (N, ktot), (w_pitch, 1), woff + b * b_batch_rows * w_pitch)
+            Wt = torch.as_strided(wbuf, (N, ktot), (w_pitch, 1),
+                                  woff + (b * b_batch_rows + hd * b_inner_rows) * w_pitch + hd * b_inner_k)
             D = A @ Wt.t()
             if softmax:
                 mx = D.max(dim=1, keepdim=True).values
                 Pm = torch.exp((D - mx) * softmax_scale)
                 if self.bf:
                     Pm = _bf16(Pm)
-                self.wr(out_bf16, Pm, (M, N), (ldc, 1)) if batch == 1 else None
                 buf, off = self.flat(out_bf16)
-                torch.as_strided(buf, (M, N), (ldc, 1), off + b * out_batch_stride).copy_(Pm)
+                torch.as_strided(buf, (M, N), (ldc, 1), off + obs).copy_(Pm)
                 rbuf, roff = self.flat(rowsum_out)
-                rbuf[roff + b * M: roff + (b + 1) * M] = Pm.sum(1)
+                rbuf[roff + bi * M: roff + (bi + 1) * M] = Pm.sum(1)
                 continue
             if rowscale is not None:
                 rbuf, roff = self.flat(rowscale)
-                D = D / rbuf[roff + b * M: roff + (b + 1) * M][:, None]
+                D = D / rbuf[roff + bi * M: roff + (bi + 1) * M][:, None]
             if bias is not None:
                 bb, boff = self.flat(bias)
                 D = D + (bb[boff:boff + M][:, None] if bias_along_m else bb[boff:boff + N][None, :])
@@ -128,13 +131,13 @@ class Interp:
                 D = F.silu(D)
             if resid is not None:
                 rb, ro = self.flat(resid)
-                D = D + torch.as_strided(rb, (M, N), (ldc, 1), ro + b * out_batch_stride)
+                D = D + torch.as_strided(rb, (M, N), (ldc, 1), ro + obs)
             D = D * alpha
             for dst in (out_f32, out_bf16):
                 if dst is not None:
                     buf, off = self.flat(dst)
                     val = _bf16(D) if (self.bf and dst.tensor.dtype == "bf16") else D
-                    torch.as_strided(buf, (M, N), (ldc, 1), off + b * out_batch_stride).copy_(val)
+                    torch.as_strided(buf, (M, N), (ldc, 1), off + obs).copy_(val)
             if stats is not None:
                 seg = min(H * W, 128)
                 nseg = M // seg
@@ -147,6 +150,15 @@ class Interp:
                     eps, silu, resample, out_bf16, raw_bf16, raw_f32):
         C = C0 + C1
         HW = H * W
+        if stats0 is None:   # identity: cast / resample only
+            y = self.rd(src0, (B, H, W, C0))
+            if resample == 1:
+                y = y.repeat_interleave(2, 1).repeat_interleave(2, 2)
+            elif resample == 2:
+                y = y.reshape(B, H // 2, 2, W // 2, 2, C).mean((2, 4))
+            Ho, Wo = y.shape[1], y.shape[2]
+            self.wr(out_bf16, y, (B, Ho, Wo, C), (Ho * Wo * C, Wo * C, C, 1))
+            return
         xs = [self.rd(src0, (B, H, W, C0))]
         sums = [self.rd(stats0, (B, P0, C0, 2)).sum(1)]
         if src1 is not None:
@@ -206,6 +218,10 @@ class Interp:
         a = self.rd(act, (B, H, W, C)).permute(0, 3, 1, 2)
         wt = self.rd(w, (3, 3, C, Cout)).permute(3, 2, 0, 1).contiguous()
         self.out = F.conv2d(a, wt, self.rd(bias, (Cout,)), padding=1)
+
+    def op_softmax_rows(self, src, out, rows, T):
+        x = self.rd(src, (rows, T))
+        self.wr(out, torch.softmax(x, -1), (rows, T), (T, 1))
 
     def op_attn_small(self, qkv, out, B, T, heads, d, scale):
         x = self.rd(qkv, (B, T, 3, heads, d))

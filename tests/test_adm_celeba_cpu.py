@@ -1,0 +1,94 @@
+"""CPU: ADM (guided_diffusion) and CelebA-HQ DDPM -- oracles vs the golden vectors generated from the reference's
+own modules / reverse steps, lowerings vs oracles through the program interpreter, schedule tables vs oracle loops."""
+import os
+
+import numpy as np
+import torch
+
+from diffpure_b200 import lowering_adm as LA, lowering_ddpm as LD, schedule
+from oracle import adm as A, ddpm_loops as OL, ddpm_unet as D, weights
+from program_interp import Interp
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+ADM_TINY = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+CELEBA_TINY = D.tiny_cfg(32, 64, (1, 2, 2), 1, (16,))
+
+
+def load(name):
+    return {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(os.path.join(G, name)).items()}
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_adm_oracle_matches_reference_golden():
+    d = load("adm_tiny.npz")
+    sd = weights.make_state_dict(A.param_shapes(ADM_TINY), seed=int(d["seed"]))
+    unet = lambda x, t: A.forward(ADM_TINY, sd, x, t)  # noqa: E731
+    assert (unet(d["x"], d["t"]) - d["y"]).abs().max().item() < 1e-5
+    out = OL.purify_guided(unet, d["x0"], int(d["t_levels"]), d["e0"], d["z"])
+    assert (out - d["loop_out"]).abs().max().item() < 1e-4
+    # the reference's fp16-torso mode differs from fp32 by ~2e-3: the bound our bf16 path is judged against
+    assert 5e-4 < rel(d["y_fp16"], d["y"]) < 1e-2
+
+
+def test_celeba_oracle_matches_reference_golden():
+    d = load("celeba_tiny.npz")
+    sd = weights.make_state_dict(D.param_shapes(CELEBA_TINY), seed=int(d["seed"]))
+    unet = lambda x, t: D.forward(CELEBA_TINY, sd, x, t)  # noqa: E731
+    assert (unet(d["x"], d["t"]) - d["y"]).abs().max().item() < 1e-5
+    out = OL.purify_celeba(unet, d["x0"], int(d["t_levels"]), d["e0"], d["z"])
+    assert (out - d["loop_out"]).abs().max().item() < 1e-5
+
+
+def test_adm_lowering_matches_oracle():
+    d = load("adm_tiny.npz")
+    sd = weights.make_state_dict(A.param_shapes(ADM_TINY), seed=int(d["seed"]))
+    assert set(LA.param_shapes(ADM_TINY).items()) == {(k, tuple(v)) for k, v in A.param_shapes(ADM_TINY).items()}
+    prog = LA.lower(ADM_TINY, sd, 2)
+    y32 = Interp(prog, emulate_bf16=False).run(d["x"], d["t"].float())
+    assert rel(y32, d["y"]) < 1e-5
+    assert rel(Interp(prog, emulate_bf16=True).run(d["x"], d["t"].float()), d["y"]) < 2e-2
+    kinds = {o.kind for o in prog.ops}
+    assert {"softmax_rows", "attn_small", "gemm", "gn_apply"} <= kinds   # T = 1024 / 256 / 64 attention paths
+
+
+def test_celeba_lowering_matches_oracle():
+    d = load("celeba_tiny.npz")
+    sd = weights.make_state_dict(D.param_shapes(CELEBA_TINY), seed=int(d["seed"]))
+    assert set(LD.param_shapes(CELEBA_TINY).items()) == {(k, tuple(v)) for k, v in D.param_shapes(CELEBA_TINY).items()}
+    prog = LD.lower(CELEBA_TINY, sd, 2)
+    assert rel(Interp(prog, emulate_bf16=False).run(d["x"], d["t"].float()), d["y"]) < 1e-5
+    assert rel(Interp(prog, emulate_bf16=True).run(d["x"], d["t"].float()), d["y"]) < 2e-2
+
+
+def test_full_size_parameter_tables():
+    n = lambda sh: sum(int(np.prod(v)) for v in sh.values())  # noqa: E731
+    assert n(LA.param_shapes(LA.imagenet_cfg())) == 552814086
+    assert n(LD.param_shapes(LD.celeba_cfg())) == 113673219
+
+
+def test_ddpm_schedules_reproduce_oracle_steps():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    e6 = torch.randn(2, 6, 8, 8, generator=g)
+    z = torch.randn(2, 3, 8, 8, generator=g)
+    tab = OL.GuidedTables()
+    cond, coef, sx, se = schedule.guided_tables(150)
+    assert len(cond) == 150 and cond[0] == 149 and cond[-1] == 0
+    for k in (0, 70, 148, 149):
+        ref = OL.guided_p_sample(lambda xx, tt: e6, tab, x, 149 - k, z)
+        c = coef[k]
+        eps, v = e6[:, :3], e6[:, 3:]
+        x0 = (c[0] * x - c[1] * eps).clamp(-1, 1)
+        frac = (v + 1) / 2
+        mine = c[2] * x0 + c[3] * x + c[6] * torch.exp(0.5 * (frac * c[4] + (1 - frac) * c[5])) * z
+        assert (ref - mine).abs().max().item() < 1e-6
+    e3 = e6[:, :3]
+    ref = OL.purify_celeba(lambda xx, tt: e3, x, 3, z, torch.stack([z, z, z]))
+    _, cf, sx3, se3 = schedule.ddpm_tables(3)
+    xx = sx3 * x + se3 * z
+    for k in range(3):
+        xx = cf[k, 0] * xx + cf[k, 1] * e3 + cf[k, 2] * z
+    assert (ref - xx).abs().max().item() < 1e-5
