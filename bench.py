@@ -36,6 +36,40 @@ import torch  # noqa: E402
 F_PER_IMAGE_EVAL = 37.09e9   # algorithmic FLOPs / image / UNet eval, DDPM++
 T_STAR = 100
 
+# BASELINE.json configs. `cifar10` (configs[1]) is the headline workload and the default; the 256x256 models
+# (configs[2..4]) are selectable for the record with --config, they are not the default bench line.
+WORKLOADS = {
+    "cifar10": dict(desc="CIFAR-10 32x32 DDPM++ VP-SDE t*=0.1, 100 Euler steps", size=32, batch=512, flops=37.09e9,
+                    metric="purified images/sec (100-step VP-SDE)"),
+    "adm": dict(desc="ImageNet 256x256 guided_diffusion ADM, 150 ancestral steps (learned-range p_sample)", size=256,
+                batch=32, flops=2239.67e9, metric="purified images/sec (150-step ADM chain)"),
+    "celeba": dict(desc="CelebA-HQ 256x256 ddpm/unet_ddpm, 100 ancestral steps", size=256, batch=16, flops=497.03e9,
+                   metric="purified images/sec (100-step DDPM chain)"),
+}
+
+
+def make_workload(name, seed=0):
+    """(lower_fn, cfg, state_dict, cond, coef, sx, se, update_kind) for a BASELINE config, random-init weights."""
+    from diffpure_b200 import lib, schedule, synthetic
+    if name == "cifar10":
+        from diffpure_b200 import lowering_ncsnpp as L
+        cfg = L.cifar10_cfg()
+        cond, coef = schedule.vpsde_tables(T_STAR)
+        sx, se = schedule.vpsde_forward_scales(T_STAR)
+        kind = lib.DP_UPDATE_LINEAR
+    elif name == "adm":
+        from diffpure_b200 import lowering_adm as L
+        cfg = L.imagenet_cfg()
+        cond, coef, sx, se = schedule.guided_tables(150)
+        kind = lib.DP_UPDATE_LEARNED_RANGE
+    else:
+        from diffpure_b200 import lowering_ddpm as L
+        cfg = L.celeba_cfg()
+        cond, coef, sx, se = schedule.ddpm_tables(100)
+        kind = lib.DP_UPDATE_LINEAR
+    sd = synthetic.random_state_dict(L.param_shapes(cfg), seed=seed)
+    return L.lower, cfg, sd, cond, coef, sx, se, kind
+
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -160,7 +194,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="images per GPU")
+    ap.add_argument("--config", default="cifar10", choices=list(WORKLOADS), help="BASELINE workload (default: headline)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (0 = the config's BASELINE batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -183,31 +218,23 @@ def main():
     from diffpure_b200.runners.diffpure_sde import RevGuidedDiffusion
     from types import SimpleNamespace
 
-    B = args.batch
+    wl = WORKLOADS[args.config]
+    B = args.batch or wl["batch"]
+    S = wl["size"]
     # ---- weights: rank 0 materialises them, one NCCL broadcast of the flat blob --------------------------
-    cfg, sd = make_weights(seed=0)
+    lower_fn, cfg, sd, cond, coef, sx, se, update_kind = make_workload(args.config, seed=0)
     if world > 1:
-        names = list(sd.keys())
-        flat = torch.cat([sd[k].reshape(-1) for k in names]).to(dev)
-        if rank != 0:
-            flat.zero_()
-        dist.broadcast(flat, src=0)
-        off, flat_cpu = 0, flat.cpu()
-        for k in names:
-            n = sd[k].numel()
-            sd[k] = flat_cpu[off:off + n].reshape(sd[k].shape).clone()
-            off += n
-    eng = Engine(L.lower(cfg, sd, B), device=local)
-    cond, coef = schedule.vpsde_tables(T_STAR)
+        from diffpure_b200.distributed import broadcast_state_dict
+        sd = broadcast_state_dict(sd, src=0, device=dev)
+    eng = Engine(lower_fn(cfg, sd, B), device=local)
     nsteps = len(cond)
-    sx, se = schedule.vpsde_forward_scales(T_STAR)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    x_host = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory()
+    x_host = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).pin_memory()
     x_dev = x_host.to(dev)
     gathered = [torch.empty_like(x_dev) for _ in range(world)] if world > 1 else None
 
     def one_step(seed):
-        out = eng.purify(x_dev, cond, coef, sx, se, seed=seed, sample_offset=rank * B)
+        out = eng.purify(x_dev, cond, coef, sx, se, update_kind=update_kind, seed=seed, sample_offset=rank * B)
         if world > 1:
             dist.all_gather(gathered, out)
         return out
@@ -242,7 +269,7 @@ def main():
 
     # ---- e2e through the runner API from pinned host memory ----------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.config == "cifar10":
         rargs = SimpleNamespace(t=T_STAR, rand_t=False, t_delta=15, use_bm=False, score_type="score_sde",
                                 sample_step=1, log_dir="/tmp/diffpure_b200_bench", save_images=False)
         rconfig = SimpleNamespace(data=SimpleNamespace(dataset="CIFAR10", image_size=32, num_channels=3),
@@ -259,7 +286,7 @@ def main():
             runner = RevGuidedDiffusion(rargs, rconfig, device=dev, state_dict=sd)
         runner.model._engines[(B, local)] = eng     # share the engine already built for this batch size
         runner.sample_offset = rank * B
-        out_host = torch.empty(B, 3, 32, 32).pin_memory()
+        out_host = torch.empty(B, 3, S, S).pin_memory()
 
         def e2e_step(seed):
             with torch.no_grad():
@@ -270,7 +297,7 @@ def main():
         e2e_step(0)
         ms_e2e = timed(e2e_step, args.steps)
         e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": B * 3 * 32 * 32 * 4, "d2h_bytes_per_step": B * 3 * 32 * 32 * 4,
+               "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * 3 * S * S * 4,
                "api": "diffpure_b200.runners.diffpure_sde.RevGuidedDiffusion.image_editing_sample"}
 
     if rank != 0:
@@ -291,7 +318,7 @@ def main():
         d[2] += fl
     gemm_n, gemm_ms, gemm_fl = by_kind["gemm"]
     eval_ms = sum(v[1] for v in by_kind.values())
-    alg_flops_eval = F_PER_IMAGE_EVAL * B
+    alg_flops_eval = wl["flops"] * B
     achieved_tf = alg_flops_eval / (gemm_ms / 1e3) / 1e12
     roofline = {"bound": "tensor", "kernel": "dp::gemm_kernel<BN,softmax> (tcgen05 implicit GEMM)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
@@ -299,24 +326,24 @@ def main():
                 "avg_launch_ms": gemm_ms / gemm_n, "alg_flops_per_launch": alg_flops_eval / gemm_n,
                 "executed_gemm_flops_per_eval": gemm_fl, "kernel_share_of_eval": gemm_ms / eval_ms,
                 "eval_ms_by_kind": {k: round(v[1], 4) for k, v in by_kind.items()},
-                "whole_loop_frac_of_peak": (value / world) * nsteps * F_PER_IMAGE_EVAL / 1e12 / peak_tf}
+                "whole_loop_frac_of_peak": (value / world) * nsteps * wl["flops"] / 1e12 / peak_tf}
     traffic_path = os.path.join(ROOT, "profiles", "gemm_dram_bytes_per_launch.json")
     if os.path.exists(traffic_path):
         with open(traffic_path) as f:
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.config == "cifar10":
         rate, dt, threads = cpu_reference_rate(8, 4)
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"oracle CPU port of the reference loop, batch 8, 4 of 100 Euler steps ({dt:.1f} s), "
                          f"extrapolated linearly"}
 
     launches = args.steps * (nsteps * (eng.launches_per_eval + 1) + 2)
-    line = {"metric": "purified images/sec (100-step VP-SDE)", "value": value, "unit": "images/s", "n_gpus": world,
+    line = {"metric": wl["metric"], "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CIFAR-10 32x32 DDPM++ VP-SDE t*=0.1, 100 Euler steps, batch %d per GPU" % B,
+            "config": {"workload": "%s, batch %d per GPU" % (wl["desc"], B),
                        "weights": "random-init (seeded factory)", "global_batch": world * B,
                        "parallelism": "dp%d" % world,
                        "l2": "per-step working set (>= 2 GB of activations) exceeds the 126 MB L2"},

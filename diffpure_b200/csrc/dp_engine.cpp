@@ -17,7 +17,8 @@ namespace {
 
 std::string g_create_error;
 
-enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL, OP_SOFTMAX };
+enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL, OP_SOFTMAX,
+              OP_GN_FINALIZE };
 
 struct StatsReduce {
   const float* in;
@@ -61,6 +62,8 @@ struct dp_engine {
   float* d_coef = nullptr;
   int table_cap = 0;
   dp::CallParams* d_call = nullptr;
+  float* gn_ss = nullptr;  // [B][2][C] scale/shift scratch shared by all GroupNorm ops (stream-ordered)
+  size_t gn_ss_floats = 0;
   cudaStream_t stream = nullptr;
   cudaGraphExec_t g_forward = nullptr, g_step = nullptr;
 };
@@ -126,7 +129,10 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s);
       break;
     case OP_GN:
-      rc = dp::launch_gn_apply(op.gn, e->num_sms, s);
+      rc = dp::launch_gn_apply(op.gn, op.gn.stats0 ? e->gn_ss : nullptr, e->num_sms, s);
+      break;
+    case OP_GN_FINALIZE:
+      rc = dp::launch_gn_finalize(op.gn, e->gn_ss, s);
       break;
     case OP_STATS:
       rc = dp::launch_stats(op.stats.src, op.stats.stats, op.stats.B, op.stats.HW, op.stats.C, s);
@@ -257,6 +263,7 @@ void dp_destroy(dp_engine* e) {
   cudaFree(e->d_cond);
   cudaFree(e->d_coef);
   cudaFree(e->d_call);
+  cudaFree(e->gn_ss);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -439,6 +446,22 @@ int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d) {
     r.sred.C = Cx;
     e->ops.push_back(r);
     if (which) { p.stats1 = r.sred.out; p.P1 = 1; } else { p.stats0 = r.sred.out; p.P0 = 1; }
+  }
+  if (p.stats0) {
+    const size_t need = static_cast<size_t>(d->B) * 2 * C;
+    if (need > e->gn_ss_floats) {
+      if (!e->ops.empty() && e->gn_ss) {
+        // earlier ops captured the old pointer by value only at launch time (read from the engine), so growing is safe
+      }
+      cudaFree(e->gn_ss);
+      e->gn_ss = nullptr;
+      DP_CUDA(e, cudaMalloc(&e->gn_ss, need * sizeof(float)));
+      e->gn_ss_floats = need;
+    }
+    Op f;
+    f.kind = OP_GN_FINALIZE;
+    f.gn = p;
+    e->ops.push_back(f);
   }
   Op op;
   op.kind = OP_GN;

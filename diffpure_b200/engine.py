@@ -220,7 +220,7 @@ class Engine:
         return out
 
     OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "conv_out", "attn_small",
-                "softmax_rows")
+                "softmax_rows", "gn_finalize")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

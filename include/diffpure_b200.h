@@ -191,7 +191,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
- * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,8 softmax_rows,
+ * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,8 softmax_rows, 9 gn_finalize,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

@@ -41,3 +41,16 @@ if os.environ.get("DP_PRINT_PROFILE"):
         seen[key][0] += 1; seen[key][1] += ms; seen[key][2] += fl
     for k, v in sorted(seen.items(), key=lambda kv: -kv[1][1]):
         print(f"gemm B{k[0]} {k[1]}x{k[2]} N={k[3]} segs={k[4]} batch={k[5]} resid={k[6]} sm={k[7]}: n={v[0]} total {v[1]:.3f} ms  {v[2]/1e12/(v[1]/1e3):.1f} TF/s")
+
+    # per-gn_apply detail (bytes = fp32 in + bf16 out (+ raw copies))
+    gn_rows = [ms for (kind, ms, fl) in rows if kind == "gn_apply"]
+    gn_ops = [o for o in prog.ops if o.kind == "gn_apply"]
+    seen = collections.OrderedDict()
+    for ms, o in zip(gn_rows, gn_ops):
+        a = o.args; C = a["C0"] + a["C1"]; H, W = a["H"], a["W"]
+        sc = {0: 1, 1: 4, 2: 0.25}[a["resample"]]
+        by = B * H * W * C * (4 + sc * 2 * (2 if a["raw_bf16"] is not None else 1) + (sc * 4 if a["raw_f32"] is not None else 0))
+        key = (H, a["C0"], a["C1"], a["resample"], a["raw_bf16"] is not None)
+        seen.setdefault(key, [0, 0.0, 0.0]); seen[key][0] += 1; seen[key][1] += ms; seen[key][2] += by
+    for k, v in sorted(seen.items(), key=lambda kv: -kv[1][1]):
+        print(f"gn H={k[0]} C0={k[1]} C1={k[2]} res={k[3]} raw={k[4]}: n={v[0]} total {v[1]:.3f} ms  {v[2]/1e9/(v[1]/1e3):.0f} GB/s")

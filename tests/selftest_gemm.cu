@@ -295,6 +295,44 @@ static void run_attention(int Bt, int T, int C, int bn_s) {
   cudaFree(d_qk); cudaFree(d_vt); cudaFree(d_p); cudaFree(d_rs); cudaFree(d_o);
 }
 
+// perf mode: time one conv shape (no host reference): selftest_gemm perf B H W C0 taps N resid
+static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, int bnforce) {
+  const size_t M = (size_t)B * H * W;
+  const int Kt = taps * C0;
+  __nv_bfloat16 *d_a, *d_w;
+  float *d_out, *d_res, *d_bias, *d_rowvec, *d_stats;
+  CK(cudaMalloc(&d_a, M * C0 * 2)); CK(cudaMemset(d_a, 0, M * C0 * 2));
+  CK(cudaMalloc(&d_w, (size_t)N * Kt * 2)); CK(cudaMemset(d_w, 0, (size_t)N * Kt * 2));
+  CK(cudaMalloc(&d_out, M * N * 4)); CK(cudaMalloc(&d_res, M * N * 4)); CK(cudaMemset(d_res, 0, M * N * 4));
+  CK(cudaMalloc(&d_bias, N * 4)); CK(cudaMemset(d_bias, 0, N * 4));
+  CK(cudaMalloc(&d_rowvec, (size_t)B * N * 4)); CK(cudaMemset(d_rowvec, 0, (size_t)B * N * 4));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = 1;
+  int bn = bnforce ? bnforce : ((N % 256 == 0) ? 256 : 128);
+  dp::gemm_fill_geometry(p, B, H, W, N, bn);
+  CK(cudaMalloc(&d_stats, (size_t)p.m_tiles * p.stat_nseg * N * 8));
+  const dp::TileBox tb = dp::gemm_tile_box(H, W);
+  std::string err;
+  if (dp::make_act_tmap(&p.a[0].tmap, d_a, C0, C0, W, H, B, tb.bw, tb.bh, tb.bn, 1, &err)) { printf("%s\n", err.c_str()); exit(1); }
+  p.a[0].taps = taps; p.a[0].kchunks = C0 / 64; p.a[0].stride = 1; p.a[0].pad = taps == 9 ? 1 : 0; p.nseg = 1;
+  if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, bn, &err)) { printf("%s\n", err.c_str()); exit(1); }
+  p.bias = d_bias; p.alpha = 1.f; p.out_f32 = d_out; p.ldc = N; p.stats = d_stats;
+  int sh = 0; while ((1 << sh) < H * W) ++sh;
+  if (resid) { p.resid = d_res; p.alpha = 0.70710678f; } else { p.rowvec = d_rowvec; p.rowvec_ld = N; p.rowvec_shift = sh; }
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) dp::launch_gemm(p, bn, false, num_sms, 0);
+  CK(cudaDeviceSynchronize());
+  const int iters = 20;
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) dp::launch_gemm(p, bn, false, num_sms, 0);
+  cudaEventRecord(e1);
+  CK(cudaEventSynchronize(e1));
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double fl = 2.0 * M * N * Kt;
+  printf("perf B%d %dx%d C%d taps%d N%d bn%d resid%d: %.1f us  %.1f TF/s\n", B, H, W, C0, taps, N, bn, resid, ms / iters * 1e3, fl / (ms / iters * 1e-3) / 1e12);
+}
+
 int main(int argc, char** argv) {
   int devid = 0;
   CK(cudaSetDevice(devid));
@@ -305,6 +343,10 @@ int main(int argc, char** argv) {
   int e = dp::gemm_init();
   if (e) { printf("gemm_init failed %d\n", e); return 2; }
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 8 && !strcmp(argv[1], "perf")) {
+    run_perf(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]), argc > 9 ? atoi(argv[9]) : 0);
+    return 0;
+  }
 
   const ConvCase cases[] = {
       // name                      B  H   W   C0  taps C1   N   bn  st  bias  rowv  resid silu  stats bf16  alpha
