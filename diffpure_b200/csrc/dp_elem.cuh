@@ -25,6 +25,7 @@ int launch_embed(const EmbedParams& p, cudaStream_t s);
 
 struct GnParams {
   const float* src0; const float* stats0; int C0, P0;
+  const __nv_bfloat16* src0h;  // bf16 source instead of src0 (single source, no resample)
   const float* src1; const float* stats1; int C1, P1;
   const float* gamma; const float* beta;
   const float* film; int film_ld;

@@ -422,6 +422,11 @@ int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d) {
   dp::GnParams p;
   std::memset(&p, 0, sizeof(p));
   p.src0 = d->src0; p.stats0 = d->stats0; p.C0 = d->C0; p.P0 = d->P0;
+  if (d->src0_is_bf16) {
+    if (d->C1 || d->resample) return fail(e, DP_ERR_INVALID, "gn: bf16 source needs a single un-resampled source");
+    p.src0h = reinterpret_cast<const __nv_bfloat16*>(d->src0);
+    p.src0 = nullptr;
+  }
   p.src1 = d->src1; p.stats1 = d->stats1; p.C1 = d->C1; p.P1 = d->P1;
   p.gamma = d->gamma; p.beta = d->beta; p.film = d->film; p.film_ld = d->film_ld;
   p.B = d->B; p.H = d->H; p.W = d->W; p.groups = d->groups; p.eps = d->eps; p.silu = d->silu;

@@ -148,7 +148,8 @@ class Engine:
                 d.softmax = a["softmax"]; d.softmax_scale = a["softmax_scale"]; d.rowsum_out = self._p(a["rowsum_out"])
                 self._check(L.dp_op_gemm(self.h, C.byref(d)), "dp_op_gemm")
             elif op.kind == "gn_apply":
-                d = _lib.GnDesc(self._p(a["src0"]), self._p(a["stats0"]), a["C0"], a["P0"], self._p(a["src1"]),
+                d = _lib.GnDesc(self._p(a["src0"]), self._p(a["stats0"]), a["C0"], a["P0"],
+                                1 if a["src0"].tensor.dtype == "bf16" else 0, self._p(a["src1"]),
                                 self._p(a["stats1"]), a["C1"], a["P1"], self._p(a["gamma"]), self._p(a["beta"]),
                                 self._p(a["film"]), a["film_ld"], a["B"], a["H"], a["W"], a["groups"], a["eps"],
                                 a["silu"], a["resample"], self._p(a["out_bf16"]), self._p(a["raw_bf16"]),

@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
 
 class GnDesc(C.Structure):
     _fields_ = [("src0", C.c_void_p), ("stats0", C.c_void_p), ("C0", C.c_int), ("P0", C.c_int),
-                ("src1", C.c_void_p), ("stats1", C.c_void_p), ("C1", C.c_int), ("P1", C.c_int),
+                ("src0_is_bf16", C.c_int), ("src1", C.c_void_p), ("stats1", C.c_void_p), ("C1", C.c_int), ("P1", C.c_int),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("film", C.c_void_p), ("film_ld", C.c_int),
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int), ("eps", C.c_float),
                 ("silu", C.c_int), ("resample", C.c_int), ("out_bf16", C.c_void_p), ("raw_bf16", C.c_void_p),

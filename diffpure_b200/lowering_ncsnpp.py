@@ -109,8 +109,10 @@ def param_shapes(cfg):
     return shapes
 
 
-def lower(cfg, sd, B):
-    """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU)."""
+def lower(cfg, sd, B, h_bf16=True):
+    """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU).
+    h_bf16: store the Conv_0 output (only ever read by GroupNorm_1) in bf16 -- halves its HBM round trip; the
+    GroupNorm statistics are still accumulated from the fp32 accumulator values."""
     S = cfg.image_size
     prog = Program(B, S, S)
     plan = module_plan(cfg)
@@ -164,10 +166,12 @@ def lower(cfg, sd, B):
                       beta=prog.const_f32(name + ".gn0.b", P(i, "GroupNorm_0.bias")),
                       B=B, H=H, W=W, groups=_groups(cin), eps=1e-6, silu=1, resample=mode, out_bf16=a0, raw_bf16=xb)
         h = new_act(prog, name + ".h", B, cout, Ho, Wo)
+        if h_bf16:
+            h.t = prog.tensor(name + ".h16", B * Ho * Wo * cout, "bf16")
         prog.gemm([act_seg(a0, cin, taps=9)], prog.const_bf16(name + ".w0", pack_conv3x3(P(i, "Conv_0.weight"))),
                   cout, 9 * cin, B, Ho, Wo, cout, bias=prog.const_f32(name + ".b0", P(i, "Conv_0.bias")),
                   rowvec=view(temb_all, dense_off[i]), rowvec_ld=n_all, rowvec_rows_per_sample=Ho * Wo,
-                  out_f32=h.t, stats=h.stats)
+                  out_f32=None if h_bf16 else h.t, out_bf16=h.t if h_bf16 else None, stats=h.stats)
         a1 = prog.tensor(name + ".a1", B * Ho * Wo * cout, "bf16")
         prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P,
                       gamma=prog.const_f32(name + ".gn1.w", P(i, "GroupNorm_1.weight")),

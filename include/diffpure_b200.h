@@ -105,6 +105,7 @@ typedef struct {
 typedef struct {
   const float* src0; const float* stats0; int C0; int P0; /* fp32 NHWC + [B][P0][C0][2] partials;
                                                              stats0 == NULL: identity (cast / resample only) */
+  int src0_is_bf16;                                       /* src0 points to bf16 data (C1 == 0, resample == 0) */
   const float* src1; const float* stats1; int C1; int P1; /* optional channel-concat second source */
   const float* gamma; const float* beta;                  /* [C0+C1] */
   const float* film; int film_ld;                         /* optional [B, film_ld]: scale = [:C], shift = [C:2C] */
