@@ -521,6 +521,58 @@ int launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-step update from the output conv's result (fp32 [B*HW, ld], first Cout columns valid)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+  const long long gp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int HW = p.H * p.W;
+  const long long npix = static_cast<long long>(p.B) * HW;
+  if (gp >= npix) return;
+  const int b = static_cast<int>(gp / HW);
+  const int pix = static_cast<int>(gp - static_cast<long long>(b) * HW);
+  const float* e = p.eps + gp * p.ld;
+  float o[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) o[j] = j < p.Cout ? e[j] : 0.f;
+  if (p.mode == 0) {
+    for (int j = 0; j < p.Cout; ++j) p.out_nchw[(static_cast<size_t>(b) * p.Cout + j) * HW + pix] = o[j];
+    return;
+  }
+  const int step = *p.tables.step;
+  const CallParams cp = *p.call;
+  float k[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k[i] = p.tables.coef[step * 8 + i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float* xp = p.x + gp * 3 + c;
+    const float xv = *xp;
+    const float z = cp.step_noise ? cp.step_noise[((static_cast<size_t>(step) * p.B + b) * 3 + c) * HW + pix]
+                                  : dp_normal(cp.seed, cp.sample_offset + b, static_cast<unsigned>(step) + 1u,
+                                              static_cast<unsigned>(pix), c);
+    float xn;
+    if (cp.update_kind == 0) {
+      xn = k[0] * xv + k[1] * o[c] + k[2] * z;
+    } else {
+      // guided_diffusion/gaussian_diffusion.py:277-284,305,317-322,438-446
+      float x0 = k[0] * xv - k[1] * o[c];
+      x0 = fminf(1.f, fmaxf(-1.f, x0));
+      const float mean = k[2] * x0 + k[3] * xv;
+      const float frac = (o[3 + c] + 1.f) * 0.5f;
+      const float logvar = frac * k[4] + (1.f - frac) * k[5];
+      xn = mean + k[6] * expf(0.5f * logvar) * z;
+    }
+    *xp = xn;
+  }
+}
+
+int launch_update(const UpdateParams& p, cudaStream_t s) {
+  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
+  update_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
 // short-sequence attention (T <= 64): one CTA per (head, sample), everything resident in smem
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_small_kernel(AttnSmallParams p) {

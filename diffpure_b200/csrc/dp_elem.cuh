@@ -67,6 +67,15 @@ struct ConvOutParams {
 };
 int launch_conv_out(const ConvOutParams& p, cudaStream_t s);
 
+// Per-step update from an fp32 eps buffer [B*H*W, ld] (written by the output conv run as a tensor-core GEMM):
+// mode 0 copies the first Cout columns to out_nchw, mode 1 applies the fused SDE / DDPM update to x (NHWC [.,3]).
+struct UpdateParams {
+  const float* eps; int ld; int B, H, W, Cout;
+  int mode; float* out_nchw; float* x;
+  StepTables tables; const CallParams* call;
+};
+int launch_update(const UpdateParams& p, cudaStream_t s);
+
 struct AttnSmallParams {
   const __nv_bfloat16* qkv; __nv_bfloat16* out; int B, T, heads, d; float scale;
 };

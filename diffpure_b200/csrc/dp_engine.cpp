@@ -18,7 +18,7 @@ namespace {
 std::string g_create_error;
 
 enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL, OP_SOFTMAX,
-              OP_GN_FINALIZE };
+              OP_GN_FINALIZE, OP_UPDATE };
 
 struct StatsReduce {
   const float* in;
@@ -39,6 +39,7 @@ struct Op {
   dp::ConvOutParams cout_;
   dp::AttnSmallParams attn;
   dp_softmax_desc smax;
+  dp::UpdateParams upd;
 };
 
 }  // namespace
@@ -158,6 +159,15 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
     case OP_ATTN_SMALL:
       rc = dp::launch_attn_small(op.attn, s);
       break;
+    case OP_UPDATE: {
+      dp::UpdateParams u = op.upd;
+      u.mode = mode;
+      u.out_nchw = e->eps_out;
+      u.x = e->x_state;
+      u.call = e->d_call;
+      rc = dp::launch_update(u, s);
+      break;
+    }
     case OP_SOFTMAX:
       rc = dp::launch_softmax_rows(op.smax.src, static_cast<__nv_bfloat16*>(op.smax.out_bf16), op.smax.rows,
                                    op.smax.T, s);
@@ -541,6 +551,21 @@ int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d) {
   Op op;
   op.kind = OP_SOFTMAX;
   op.smax = *d;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_update(dp_engine* e, const dp_update_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (int rc = ensure_run_state(e)) return rc;
+  if ((d->Cout != 3 && d->Cout != 6) || d->ld < d->Cout) return fail(e, DP_ERR_INVALID, "update: Cout in {3,6}, ld >= Cout");
+  Op op;
+  op.kind = OP_UPDATE;
+  std::memset(&op.upd, 0, sizeof(op.upd));
+  op.upd.eps = d->eps; op.upd.ld = d->ld; op.upd.B = d->B; op.upd.H = d->H; op.upd.W = d->W; op.upd.Cout = d->Cout;
+  op.upd.tables = tables_of(e, 8);
+  e->Cout = d->Cout;
   e->ops.push_back(op);
   return DP_OK;
 }

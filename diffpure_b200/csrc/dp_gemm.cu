@@ -479,6 +479,8 @@ int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   X(E_BIAS_N | E_F32)                                           \
   X(E_BIAS_M | E_BF16)                                          \
   X(E_ROWSCALE | E_BF16)                                        \
+  X(E_BF16)                                                     \
+  X(E_F32 | E_ALPHA)                                            \
   X(E_GENERIC)                                                  \
   X(E_SOFTMAX)
 

@@ -167,6 +167,9 @@ class Engine:
                 d = _lib.AttnSmallDesc(self._p(a["qkv"]), self._p(a["out"]), a["B"], a["T"], a["heads"], a["d"],
                                        a["scale"])
                 self._check(L.dp_op_attn_small(self.h, C.byref(d)), "dp_op_attn_small")
+            elif op.kind == "update":
+                d = _lib.UpdateDesc(self._p(a["eps"]), a["ld"], a["B"], a["H"], a["W"], a["Cout"])
+                self._check(L.dp_op_update(self.h, C.byref(d)), "dp_op_update")
             elif op.kind == "softmax_rows":
                 d = _lib.SoftmaxDesc(self._p(a["src"]), self._p(a["out"]), a["rows"], a["T"])
                 self._check(L.dp_op_softmax_rows(self.h, C.byref(d)), "dp_op_softmax_rows")
@@ -221,7 +224,7 @@ class Engine:
         return out
 
     OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "conv_out", "attn_small",
-                "softmax_rows", "gn_finalize")
+                "softmax_rows", "gn_finalize", "update")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

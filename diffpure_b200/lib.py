@@ -65,6 +65,10 @@ class SoftmaxDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("out_bf16", C.c_void_p), ("rows", C.c_longlong), ("T", C.c_int)]
 
 
+class UpdateDesc(C.Structure):
+    _fields_ = [("eps", C.c_void_p), ("ld", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int)]
+
+
 class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
@@ -92,6 +96,7 @@ SYMBOLS = {
     "dp_op_conv_out": (C.c_int, [C.c_void_p, C.POINTER(ConvOutDesc)]),
     "dp_op_attn_small": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallDesc)]),
     "dp_op_softmax_rows": (C.c_int, [C.c_void_p, C.POINTER(SoftmaxDesc)]),
+    "dp_op_update": (C.c_int, [C.c_void_p, C.POINTER(UpdateDesc)]),
     "dp_program_size": (C.c_int, [C.c_void_p]),
     "dp_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "dp_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -116,7 +116,8 @@ def param_shapes(cfg):
     return sh
 
 
-def lower(cfg, sd, B):
+def lower(cfg, sd, B, h_bf16=True):
+    """h_bf16: the first conv's output (read only by the second GroupNorm) is stored in bf16."""
     S = cfg.image_size
     prog = Program(B, S, S)
     mc, emb_dim = cfg.model_channels, cfg.model_channels * 4
@@ -165,9 +166,11 @@ def lower(cfg, sd, B):
                       beta=prog.const_f32(p + "n0.b", P(p + "in_layers.0.bias")), B=B, H=H, W=W, groups=32, eps=EPS,
                       silu=1, resample=mode, out_bf16=a0, raw_bf16=xb, raw_f32=xr)
         h = new_act(prog, p + "h", B, cout, Ho, Wo)
+        if h_bf16:
+            h.t = prog.tensor(p + "h16", B * Ho * Wo * cout, "bf16")
         prog.gemm([act_seg(a0, cin, taps=9)], prog.const_bf16(p + "w0", pack_conv3x3(P(p + "in_layers.2.weight"))),
                   cout, 9 * cin, B, Ho, Wo, cout, bias=prog.const_f32(p + "b0", P(p + "in_layers.2.bias")),
-                  out_f32=h.t, stats=h.stats)
+                  out_f32=None if h_bf16 else h.t, out_bf16=h.t if h_bf16 else None, stats=h.stats)
         a1 = prog.tensor(p + "a1", B * Ho * Wo * cout, "bf16")
         prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P,
                       gamma=prog.const_f32(p + "n1.w", P(p + "out_layers.0.weight")),
@@ -237,7 +240,6 @@ def lower(cfg, sd, B):
     prog.gn_apply(src0=h.t, stats0=h.stats, C0=h.C, P0=h.P, gamma=prog.const_f32("out.n.w", P("out.0.weight")),
                   beta=prog.const_f32("out.n.b", P("out.0.bias")), B=B, H=S, W=S, groups=32, eps=EPS, silu=1,
                   out_bf16=a)
-    prog.conv_out(a, prog.const_f32("out.w", pack_conv_out(P("out.2.weight"))), prog.const_f32("out.b", P("out.2.bias")),
-                  B, S, S, h.C, cfg.out_channels)
+    prog.conv_out_gemm("out", a, P("out.2.weight"), P("out.2.bias"), B, S, S, h.C, cfg.out_channels)
     prog.meta.update(model="adm", out_channels=cfg.out_channels, cond="timestep")
     return prog

@@ -97,7 +97,8 @@ def param_shapes(cfg):
     return sh
 
 
-def lower(cfg, sd, B):
+def lower(cfg, sd, B, h_bf16=True):
+    """h_bf16: conv1's output (read only by norm2) is stored in bf16."""
     S = cfg.image_size
     prog = Program(B, S, S)
     ch, temb_dim = cfg.ch, cfg.ch * 4
@@ -141,10 +142,12 @@ def lower(cfg, sd, B):
                       beta=prog.const_f32(p + "n1.b", P(p + "norm1.bias")), B=B, H=H, W=W, groups=32, eps=EPS, silu=1,
                       out_bf16=a0, raw_bf16=xb)
         h = new_act(prog, p + "h", B, cout, H, W)
+        if h_bf16:
+            h.t = prog.tensor(p + "h16", B * H * W * cout, "bf16")
         prog.gemm([act_seg(a0, cin, taps=9)], prog.const_bf16(p + "w1", pack_conv3x3(P(p + "conv1.weight"))), cout,
                   9 * cin, B, H, W, cout, bias=prog.const_f32(p + "b1", P(p + "conv1.bias")),
-                  rowvec=view(temb_all, dense_off[p]), rowvec_ld=n_all, rowvec_rows_per_sample=H * W, out_f32=h.t,
-                  stats=h.stats)
+                  rowvec=view(temb_all, dense_off[p]), rowvec_ld=n_all, rowvec_rows_per_sample=H * W,
+                  out_f32=None if h_bf16 else h.t, out_bf16=h.t if h_bf16 else None, stats=h.stats)
         a1 = prog.tensor(p + "a1", B * H * W * cout, "bf16")
         prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P,
                       gamma=prog.const_f32(p + "n2.w", P(p + "norm2.weight")),
@@ -229,7 +232,6 @@ def lower(cfg, sd, B):
     prog.gn_apply(src0=h.t, stats0=h.stats, C0=h.C, P0=h.P, gamma=prog.const_f32("out.n.w", P("norm_out.weight")),
                   beta=prog.const_f32("out.n.b", P("norm_out.bias")), B=B, H=S, W=S, groups=32, eps=EPS, silu=1,
                   out_bf16=a)
-    prog.conv_out(a, prog.const_f32("out.w", pack_conv_out(P("conv_out.weight"))),
-                  prog.const_f32("out.b", P("conv_out.bias")), B, S, S, h.C, cfg.out_ch)
+    prog.conv_out_gemm("out", a, P("conv_out.weight"), P("conv_out.bias"), B, S, S, h.C, cfg.out_ch)
     prog.meta.update(model="ddpm", out_channels=cfg.out_ch, cond="timestep")
     return prog

@@ -275,8 +275,7 @@ def lower(cfg, sd, B, h_bf16=True):
                   beta=prog.const_f32("out.gn.b", P(idx, "bias")), B=B, H=S, W=S, groups=_groups(C), eps=1e-6,
                   silu=1, out_bf16=a)
     idx += 1
-    prog.conv_out(a, prog.const_f32("out.w", pack_conv_out(P(idx, "weight"))), prog.const_f32("out.b", P(idx, "bias")),
-                  B, S, S, C, cfg.num_channels)
+    prog.conv_out_gemm("out", a, P(idx, "weight"), P(idx, "bias"), B, S, S, C, cfg.num_channels)
     idx += 1
     assert idx == len(plan)
     prog.meta.update(model="ncsnpp", out_channels=cfg.num_channels, cond="999*t")

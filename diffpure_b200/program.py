@@ -116,6 +116,20 @@ class Program:
     def conv_out(self, act, w, bias, B, H, W, C, Cout):
         self.add("conv_out", act=view(act), w=view(w), bias=view(bias), B=B, H=H, W=W, C=C, Cout=Cout)
 
+    def update(self, eps, ld, B, H, W, Cout):
+        self.add("update", eps=view(eps), ld=ld, B=B, H=H, W=W, Cout=Cout)
+
+    def conv_out_gemm(self, name, act, w_oc33, bias, B, H, W, C, Cout):
+        """The C->3|6 output conv on the tensor cores (N padded to 8 columns; rows >= Cout of the weight matrix are
+        read as zeros through TMA out-of-bounds fill) followed by the fused per-step update."""
+        import torch
+        from .lowering_common import act_seg, pack_conv3x3
+        eps = self.tensor(name + ".eps", B * H * W * 8, "f32")
+        b8 = torch.cat([bias.detach().float().cpu(), torch.zeros(8 - Cout)])
+        self.gemm([act_seg(act, C, taps=9)], self.const_bf16(name + ".w", pack_conv3x3(w_oc33)), Cout, 9 * C, B, H, W, 8,
+                  bias=self.const_f32(name + ".b", b8), out_f32=eps, ldc=8)
+        self.update(eps, 8, B, H, W, Cout)
+
     def attn_small(self, qkv, out, B, T, heads, d, scale):
         self.add("attn_small", qkv=view(qkv), out=view(out), B=B, T=T, heads=heads, d=d, scale=float(scale))
 

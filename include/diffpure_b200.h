@@ -143,6 +143,13 @@ typedef struct {
   int B, H, W, C, Cout; /* Cout = 3 or 6 */
 } dp_conv_out_desc;
 
+/* Output stage when the C->3|6 conv runs as a dp_op_gemm (N padded to 8): consumes its fp32 result and either
+ * returns it (dp_unet_forward) or applies the fused per-step update of dp_purify. Alternative to dp_op_conv_out. */
+typedef struct {
+  const float* eps; int ld; /* fp32 [B*H*W, ld], first Cout columns valid */
+  int B, H, W, Cout;
+} dp_update_desc;
+
 typedef struct {
   const void* qkv_bf16; /* [B*T, 3*heads*d]: q | k | v, each [heads][d] */
   void* out_bf16;       /* [B*T, heads*d] */
@@ -158,6 +165,7 @@ int dp_op_conv_in(dp_engine* e, const dp_conv_in_desc* d);
 int dp_op_conv_out(dp_engine* e, const dp_conv_out_desc* d);
 int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d);
 int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d);
+int dp_op_update(dp_engine* e, const dp_update_desc* d);
 int dp_program_size(const dp_engine* e);
 
 /* Freeze the program for images of [B, C=3, H, W]; captures the CUDA graphs. */
@@ -192,7 +200,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
- * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,8 softmax_rows, 9 gn_finalize,
+ * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,8 softmax_rows, 9 gn_finalize, 10 update,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

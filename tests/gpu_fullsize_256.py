@@ -48,6 +48,15 @@ tot = sum(v[1] for v in agg.values())
 for k, v in agg.items():
     print(f"{k:12s} n={v[0]:4d} ms={v[1]:9.3f} TF/s={(v[2] / 1e12 / (v[1] / 1e3) if v[1] else 0):8.1f}")
 print("eval total %.2f ms -> %.1f TF/s algorithmic (%.3f of 1416.5)" % (tot, B * F / tot / 1e9, B * F / tot / 1e9 / 1416.5))
+gemm_rows = [(ms, fl) for (kind, ms, fl) in rows if kind == "gemm"]
+gemm_ops = [o for o in eng.program.ops if o.kind == "gemm"]
+seen = collections.OrderedDict()
+for (ms, fl), o in zip(gemm_rows, gemm_ops):
+    a = o.args
+    key = (a["B"], a["H"], a["W"], a["N"], tuple((s.C, s.taps) for s in a["a"]), a["batch"], bool(a["resid"]), a["softmax"], a["out_bf16"] is not None)
+    seen.setdefault(key, [0, 0.0, 0.0]); seen[key][0] += 1; seen[key][1] += ms; seen[key][2] += fl
+for k, v in sorted(seen.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"gemm B{k[0]} {k[1]}x{k[2]} N={k[3]} segs={k[4]} batch={k[5]} resid={k[6]} sm={k[7]} bf16={k[8]}: n={v[0]} total {v[1]:.3f} ms  {v[2]/1e12/(v[1]/1e3):.1f} TF/s")
 n = 6
 torch.cuda.synchronize(); t0 = time.time()
 out = eng.purify(x, cond[:n], coef[:n], sx, se, update_kind=kind, seed=1)

@@ -103,8 +103,10 @@ class Interp:
             A = torch.cat([self._a_matrix(s, B, H, W, b, a_batch_rows, hd * a_inner_k + hd * a_inner_rows * s.c_total)
                            for s in a], 1)
             wbuf, woff = self.flat(w)
-            Wt = torch.as_strided(wbuf, (N, ktot), (w_pitch, 1),
-                                  woff + (b * b_batch_rows + hd * b_inner_rows) * w_pitch + hd * b_inner_k)
+            row0 = b * b_batch_rows + hd * b_inner_rows
+            nvalid = max(0, min(N, w_rows - row0))          # rows past the matrix read as zeros (TMA OOB fill)
+            Wt = torch.zeros(N, ktot)
+            Wt[:nvalid] = torch.as_strided(wbuf, (nvalid, ktot), (w_pitch, 1), woff + row0 * w_pitch + hd * b_inner_k)
             D = A @ Wt.t()
             if softmax:
                 mx = D.max(dim=1, keepdim=True).values
@@ -218,6 +220,10 @@ class Interp:
         a = self.rd(act, (B, H, W, C)).permute(0, 3, 1, 2)
         wt = self.rd(w, (3, 3, C, Cout)).permute(3, 2, 0, 1).contiguous()
         self.out = F.conv2d(a, wt, self.rd(bias, (Cout,)), padding=1)
+
+    def op_update(self, eps, ld, B, H, W, Cout):
+        e = self.rd(eps, (B, H, W, Cout), (H * W * ld, W * ld, ld, 1))
+        self.out = e.permute(0, 3, 1, 2).contiguous()
 
     def op_softmax_rows(self, src, out, rows, T):
         x = self.rd(src, (rows, T))
