@@ -339,6 +339,8 @@ int launch_stats_reduce(const float* in, float* out, int B, int P, int C, cudaSt
 // ------------------------------------------------------------------------------------------------
 // input conv 3 -> Cout (fp32 SIMT: K = 27 is too thin for the tensor pipe)
 // ------------------------------------------------------------------------------------------------
+// Each thread computes 4 consecutive pixels (along W) x 4 output channels: the 3 x 6 x 3 input patch lives in
+// registers and every 16-byte weight load from shared memory feeds 16 FMAs.
 __global__ void __launch_bounds__(256) conv_in_kernel(ConvInParams p) {
   extern __shared__ float sw[];  // [27][Cout] + bias[Cout]
   const int Cout = p.Cout;
@@ -346,41 +348,56 @@ __global__ void __launch_bounds__(256) conv_in_kernel(ConvInParams p) {
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = p.bias[i];
   __syncthreads();
   const int vpp = Cout / 4;
-  const int ppb = blockDim.x / vpp;
+  const int gpb = blockDim.x / vpp;  // 4-pixel groups per block
   const int HW = p.H * p.W;
-  const long long gp = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / vpp;
-  if (gp >= static_cast<long long>(p.B) * HW) return;
+  const int wq = p.W / 4;
+  const long long ngroups = static_cast<long long>(p.B) * p.H * wq;
+  const long long gg = static_cast<long long>(blockIdx.x) * gpb + threadIdx.x / vpp;
+  if (gg >= ngroups) return;
   const int co = (threadIdx.x % vpp) * 4;
-  const int b = static_cast<int>(gp / HW);
-  const int rem = static_cast<int>(gp - static_cast<long long>(b) * HW);
-  const int h = rem / p.W, w = rem - h * p.W;
-  float4 acc = *reinterpret_cast<const float4*>(sw + 27 * Cout + co);
+  const int b = static_cast<int>(gg / (p.H * wq));
+  const int rem = static_cast<int>(gg - static_cast<long long>(b) * p.H * wq);
+  const int h = rem / wq, w0 = (rem - h * wq) * 4;
+  float xin[3][6][3];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int hh = h + ky - 1;
-    if (hh < 0 || hh >= p.H) continue;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ww = w + kx - 1;
-      if (ww < 0 || ww >= p.W) continue;
-      const float* xin = p.x + (static_cast<size_t>(b) * HW + static_cast<size_t>(hh) * p.W + ww) * 3;
+    for (int j = 0; j < 6; ++j) {
+      const int ww = w0 + j - 1;
+      const bool ok = hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+      const float* src = p.x + (static_cast<size_t>(b) * HW + static_cast<size_t>(ok ? hh : 0) * p.W + (ok ? ww : 0)) * 3;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float xv = xin[ci];
-        const float4 wv = *reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * Cout + co);
-        acc.x += xv * wv.x; acc.y += xv * wv.y; acc.z += xv * wv.z; acc.w += xv * wv.w;
-      }
+      for (int ci = 0; ci < 3; ++ci) xin[ky][j][ci] = ok ? __ldg(src + ci) : 0.f;
     }
   }
-  *reinterpret_cast<float4*>(p.out + gp * Cout + co) = acc;
+  const float4 bias4 = *reinterpret_cast<const float4*>(sw + 27 * Cout + co);
+  float4 acc[4] = {bias4, bias4, bias4, bias4};
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float4 wv = *reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * Cout + co);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float xv = xin[ky][px + kx][ci];
+          acc[px].x += xv * wv.x; acc[px].y += xv * wv.y; acc[px].z += xv * wv.z; acc[px].w += xv * wv.w;
+        }
+      }
+  float* out = p.out + (static_cast<size_t>(b) * HW + static_cast<size_t>(h) * p.W + w0) * Cout + co;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) *reinterpret_cast<float4*>(out + static_cast<size_t>(px) * Cout) = acc[px];
 }
 
 int launch_conv_in(const ConvInParams& p, cudaStream_t s) {
+  if (p.W % 4) return static_cast<int>(cudaErrorInvalidValue);
   const int vpp = p.Cout / 4;
-  const int ppb = 256 / vpp;
-  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
+  const int gpb = 256 / vpp;
+  const long long ngroups = static_cast<long long>(p.B) * p.H * (p.W / 4);
   const size_t smem = static_cast<size_t>(28 * p.Cout) * sizeof(float);
-  conv_in_kernel<<<static_cast<unsigned>((npix + ppb - 1) / ppb), 256, smem, s>>>(p);
+  conv_in_kernel<<<static_cast<unsigned>((ngroups + gpb - 1) / gpb), 256, smem, s>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -355,6 +355,8 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   if (op.softmax) {
     if (d->N != 128 && d->N != 256) return fail(e, DP_ERR_INVALID, "gemm softmax: N must be 128 or 256");
     bn = d->N;
+  } else if (d->N <= 32 && !d->stats) {
+    bn = 32;  // narrow output (the C->3|6 conv padded to 8 columns): 128x32 tiles waste 4x instead of 16x of the MMA
   } else if (d->N % 256 == 0) {
     dp::GemmParams probe;
     std::memset(&probe, 0, sizeof(probe));

@@ -510,7 +510,7 @@ int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 size_t gemm_smem_bytes(int bn, int stages) {
-  return bn == 256 ? Smem<256>::total(stages) : Smem<128>::total(stages);
+  return bn == 256 ? Smem<256>::total(stages) : (bn == 32 ? Smem<32>::total(stages) : Smem<128>::total(stages));
 }
 
 int gemm_max_stages(int bn) {
@@ -531,6 +531,13 @@ int gemm_init() {
   if (e != cudaSuccess) return static_cast<int>(e);
   DP_EPI_LIST(X)
 #undef X
+  // narrow-N tile (output conv, N <= 32): only the plain bias epilogue and the generic fallback
+  e = cudaFuncSetAttribute(gemm_kernel<32, E_BIAS_N | E_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(gemm_kernel<32, E_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
+  if (e != cudaSuccess) return static_cast<int>(e);
   return 0;
 }
 
@@ -579,6 +586,10 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn) {
 
 int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream) {
   const int mask = softmax ? E_SOFTMAX : epi_mask_of(p);
+  if (bn == 32) {
+    if (mask == (E_BIAS_N | E_F32)) return launch_t<32, E_BIAS_N | E_F32>(p, num_sms, stream);
+    return launch_t<32, E_GENERIC>(p, num_sms, stream);
+  }
   return bn == 256 ? dispatch<256>(p, mask, num_sms, stream) : dispatch<128>(p, mask, num_sms, stream);
 }
 

@@ -354,6 +354,7 @@ int main(int argc, char** argv) {
       {"gemm 300x256x512 bn256",   1, 1, 300, 512, 1,  0, 256, 256, 1, true, false,false,false,false,true,  1.f},
       {"gemm M=16 (temb-like)",    1, 1, 16,  128, 1,  0, 512, 256, 1, true, false,false,true, false,true,  1.f},
       {"gemm M=3 N=192",           1, 1, 3,   128, 1,  0, 192, 128, 1, true, false,false,false,false,true,  1.f},
+      {"conv3x3 32x32 128->8 bn32", 2, 32, 32, 128, 9,  0, 8,   32,  1, true, false,false,false,false,false, 1.f},
       {"conv3x3 32x32 128->128",   2, 32, 32, 128, 9,  0, 128, 128, 1, true, true, true, false,true, false, 0.70710678f},
       {"conv3x3 16x16 256->256",   4, 16, 16, 256, 9,  0, 256, 256, 1, true, true, false,false,true, true,  1.f},
       {"conv3x3 8x8 256->256",     5, 8,  8,  256, 9,  0, 256, 128, 1, true, true, true, false,true, false, 0.70710678f},
