@@ -570,6 +570,9 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     float xn;
     if (cp.update_kind == 0) {
       xn = k[0] * xv + k[1] * o[c] + k[2] * z;
+    } else if (cp.update_kind == 2) {
+      // Langevin-dynamics SDE (runners/diffpure_ldsde.py:92-131): extra pull towards the initial image
+      xn = k[0] * xv + k[1] * o[c] + k[2] * z + k[3] * p.x_init[gp * 3 + c];
     } else {
       // guided_diffusion/gaussian_diffusion.py:277-284,305,317-322,438-446
       float x0 = k[0] * xv - k[1] * o[c];

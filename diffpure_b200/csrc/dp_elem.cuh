@@ -52,7 +52,7 @@ int launch_conv_in(const ConvInParams& p, cudaStream_t s);
 struct CallParams {
   const float* step_noise;  // [steps,B,3,H,W] standard normals, or null -> counter-based generator
   unsigned long long seed, sample_offset;
-  int update_kind;  // 0: x <- k0 x + k1 eps + k2 z ; 1: learned-range DDPM step
+  int update_kind;  // 0: x <- k0 x + k1 eps + k2 z ; 1: learned-range DDPM step ; 2: kind 0 + k3 x_init
 };
 
 struct ConvOutParams {
@@ -71,7 +71,7 @@ int launch_conv_out(const ConvOutParams& p, cudaStream_t s);
 // mode 0 copies the first Cout columns to out_nchw, mode 1 applies the fused SDE / DDPM update to x (NHWC [.,3]).
 struct UpdateParams {
   const float* eps; int ld; int B, H, W, Cout;
-  int mode; float* out_nchw; float* x;
+  int mode; float* out_nchw; float* x; const float* x_init;
   StepTables tables; const CallParams* call;
 };
 int launch_update(const UpdateParams& p, cudaStream_t s);

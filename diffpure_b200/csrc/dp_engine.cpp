@@ -56,6 +56,7 @@ struct dp_engine {
   int B = 0, H = 0, W = 0, Cout = 0;
   // engine-owned run state
   float* x_state = nullptr;          // NHWC fp32 [B,H,W,3]
+  float* x_init = nullptr;           // copy of the initial state (anchor of the Langevin-dynamics update)
   float* eps_out = nullptr;          // NCHW fp32 [B,Cout,H,W]
   float* cond_per_sample = nullptr;  // [B]
   int* d_step = nullptr;
@@ -164,6 +165,7 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       u.mode = mode;
       u.out_nchw = e->eps_out;
       u.x = e->x_state;
+      u.x_init = e->x_init;
       u.call = e->d_call;
       rc = dp::launch_update(u, s);
       break;
@@ -267,6 +269,7 @@ void dp_destroy(dp_engine* e) {
   if (e->g_step) cudaGraphExecDestroy(e->g_step);
   for (void* p : e->buffers) cudaFree(p);
   cudaFree(e->x_state);
+  cudaFree(e->x_init);
   cudaFree(e->eps_out);
   cudaFree(e->cond_per_sample);
   cudaFree(e->d_step);
@@ -581,6 +584,8 @@ int dp_finalize(dp_engine* e, int B, int H, int W) {
   const size_t hw = static_cast<size_t>(H) * W;
   DP_CUDA(e, cudaMalloc(&e->x_state, B * hw * 3 * sizeof(float)));
   DP_CUDA(e, cudaMemset(e->x_state, 0, B * hw * 3 * sizeof(float)));
+  DP_CUDA(e, cudaMalloc(&e->x_init, B * hw * 3 * sizeof(float)));
+  DP_CUDA(e, cudaMemset(e->x_init, 0, B * hw * 3 * sizeof(float)));
   DP_CUDA(e, cudaMalloc(&e->eps_out, B * hw * e->Cout * sizeof(float)));
   DP_CUDA(e, cudaMalloc(&e->cond_per_sample, sizeof(float) * B));
   DP_CUDA(e, cudaMemset(e->cond_per_sample, 0, sizeof(float) * B));
@@ -619,8 +624,9 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
   if (p->steps <= 0 || p->steps > e->table_cap) return fail(e, DP_ERR_INVALID, "steps out of range");
   if (p->ncoef < 3 || p->ncoef > 8) return fail(e, DP_ERR_INVALID, "ncoef out of range");
+  if (p->update_kind < 0 || p->update_kind > 2) return fail(e, DP_ERR_INVALID, "unknown update_kind");
   const int want = p->update_kind == DP_UPDATE_LEARNED_RANGE ? 6 : 3;
-  if (e->Cout != want && !(p->update_kind == DP_UPDATE_LINEAR && e->Cout == 6))
+  if (e->Cout != want && !(p->update_kind != DP_UPDATE_LEARNED_RANGE && e->Cout == 6))
     return fail(e, DP_ERR_INVALID, "update_kind does not match the model's output channels");
   cudaStream_t user = static_cast<cudaStream_t>(stream);
   DP_CUDA(e, cudaSetDevice(e->device));
@@ -646,6 +652,14 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
                                  p->seed, p->sample_offset, s);
   if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
+  if (p->update_kind == DP_UPDATE_LINEAR_ANCHORED) {
+    if (p->anchor) {
+      rc = dp::launch_init_state(p->anchor, p->anchor, e->x_init, e->B, 3, HW, 1.f, 0.f, p->seed, p->sample_offset, s);
+      if (rc) return fail(e, DP_ERR_CUDA, "anchor layout launch failed");
+    } else {
+      DP_CUDA(e, cudaMemcpyAsync(e->x_init, e->x_state, sizeof(float) * e->B * HW * 3, cudaMemcpyDeviceToDevice, s));
+    }
+  }
   for (int i = 0; i < p->steps; ++i) DP_CUDA(e, cudaGraphLaunch(e->g_step, s));
   rc = dp::launch_nhwc_to_nchw(e->x_state, out_nchw, e->B, 3, HW, s);
   if (rc) return fail(e, DP_ERR_CUDA, "nhwc_to_nchw launch failed");

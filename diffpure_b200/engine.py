@@ -200,7 +200,7 @@ class Engine:
         return out
 
     def purify(self, x0, cond, coef, init_scale_x, init_scale_e, *, update_kind=_lib.DP_UPDATE_LINEAR,
-               init_noise=None, step_noise=None, seed=0, sample_offset=0):
+               init_noise=None, step_noise=None, seed=0, sample_offset=0, anchor=None):
         """Runs the whole loop on the device. cond: [steps] host floats; coef: [steps, ncoef] host floats."""
         x0 = self._prep(x0)
         cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float32))
@@ -213,12 +213,15 @@ class Engine:
         if step_noise is not None:
             step_noise = step_noise.to(device=self._dev(), dtype=torch.float32).contiguous()
             assert step_noise.shape == (steps,) + tuple(x0.shape)
+        if anchor is not None:
+            anchor = self._prep(anchor)
+            assert anchor.shape == x0.shape
         out = torch.empty_like(x0)
         p = _lib.PurifyParams(steps, update_kind, coef.shape[1], cond.ctypes.data, coef.ctypes.data,
                               float(init_scale_x), float(init_scale_e),
                               init_noise.data_ptr() if init_noise is not None else None,
                               step_noise.data_ptr() if step_noise is not None else None, int(seed),
-                              int(sample_offset))
+                              int(sample_offset), anchor.data_ptr() if anchor is not None else None)
         torch.cuda.current_stream(self._dev()).synchronize()
         self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), None), "dp_purify")
         return out

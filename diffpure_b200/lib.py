@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libdiffpure_b200.so")
 
 DP_UPDATE_LINEAR = 0
 DP_UPDATE_LEARNED_RANGE = 1
+DP_UPDATE_LINEAR_ANCHORED = 2
 
 
 class EmbedDesc(C.Structure):
@@ -73,7 +74,7 @@ class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
                 ("init_noise", C.c_void_p), ("step_noise", C.c_void_p), ("seed", C.c_uint64),
-                ("sample_offset", C.c_uint64)]
+                ("sample_offset", C.c_uint64), ("anchor", C.c_void_p)]
 
 
 # every symbol include/diffpure_b200.h declares: name -> (restype, argtypes)

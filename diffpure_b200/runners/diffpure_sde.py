@@ -115,6 +115,31 @@ def _load_score_sde_state(path, device="cpu"):
     return sd
 
 
+def build_score_model(config, state_dict=None):
+    """Dataset -> engine-backed score model, as runners/diffpure_sde.py:160-187 (shared by the SDE / ODE / LDSDE
+    runners, which load the same checkpoints)."""
+    if config.data.dataset == 'ImageNet':
+        from .. import lowering_adm
+        img_shape = (3, 256, 256)
+        model_dir = 'pretrained/guided_diffusion'
+        cfg = lowering_adm.cfg_from_reference(config)
+        img_shape = (3, cfg.image_size, cfg.image_size)
+        if state_dict is None:
+            state_dict = torch.load(f'{model_dir}/256x256_diffusion_uncond.pt', map_location='cpu')
+        model = ScoreModel("adm", cfg, state_dict, lowering_adm.lower, out_channels=6)
+    elif config.data.dataset == 'CIFAR10':
+        from .. import lowering_ncsnpp
+        model_dir = 'pretrained/score_sde'
+        cfg = lowering_ncsnpp.cfg_from_reference(config)
+        img_shape = (cfg.num_channels, cfg.image_size, cfg.image_size)
+        if state_dict is None:
+            state_dict = _load_score_sde_state(f'{model_dir}/checkpoint_8.pth')
+        model = ScoreModel("ncsnpp", cfg, state_dict, lowering_ncsnpp.lower, out_channels=cfg.num_channels)
+    else:
+        raise NotImplementedError(f'Unknown dataset {config.data.dataset}!')
+    return model, img_shape
+
+
 class RevGuidedDiffusion(torch.nn.Module):
     def __init__(self, args, config, device=None, state_dict=None):
         """Same arguments as the reference (L151); `state_dict` optionally supplies the UNet weights
@@ -126,26 +151,7 @@ class RevGuidedDiffusion(torch.nn.Module):
             device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
         self.device = torch.device(device)
 
-        if config.data.dataset == 'ImageNet':
-            from .. import lowering_adm
-            img_shape = (3, 256, 256)
-            model_dir = 'pretrained/guided_diffusion'
-            cfg = lowering_adm.cfg_from_reference(config)
-            if state_dict is None:
-                state_dict = torch.load(f'{model_dir}/256x256_diffusion_uncond.pt', map_location='cpu')
-            model = ScoreModel("adm", cfg, state_dict, lowering_adm.lower, out_channels=6)
-        elif config.data.dataset == 'CIFAR10':
-            from .. import lowering_ncsnpp
-            img_shape = (3, 32, 32)
-            model_dir = 'pretrained/score_sde'
-            cfg = lowering_ncsnpp.cfg_from_reference(config)
-            img_shape = (cfg.num_channels, cfg.image_size, cfg.image_size)
-            if state_dict is None:
-                state_dict = _load_score_sde_state(f'{model_dir}/checkpoint_8.pth')
-            model = ScoreModel("ncsnpp", cfg, state_dict, lowering_ncsnpp.lower, out_channels=cfg.num_channels)
-        else:
-            raise NotImplementedError(f'Unknown dataset {config.data.dataset}!')
-
+        model, img_shape = build_score_model(config, state_dict)
         model.eval()
         self.model = model
         self.img_shape = img_shape

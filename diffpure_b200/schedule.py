@@ -116,3 +116,55 @@ def ddpm_tables(t_levels, beta_start=0.0001, beta_end=0.02, n=1000, var_type="fi
     coef = torch.stack([c0, c1, c2], 1).numpy().astype(np.float32)
     cond = idx.astype(np.float32)
     return cond, coef, float(ac[t_levels - 1].sqrt()), float((1.0 - ac[t_levels - 1]).sqrt())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sibling runners on the same engine
+# ---------------------------------------------------------------------------------------------------------
+def _sigma(s, score_type):
+    if score_type == "score_sde":
+        return torch.sqrt(1. - torch.exp(2. * (-0.25 * s ** 2 * (BETA_MAX - BETA_MIN) - 0.5 * s * BETA_MIN)))
+    if score_type == "guided_diffusion":
+        return torch.sqrt(1. - torch.exp(-0.5 * (BETA_MAX - BETA_MIN) * s ** 2 - BETA_MIN * s))
+    raise NotImplementedError(f"Unknown score type in RevVPSDE: {score_type}!")
+
+
+def _cond(s, score_type):
+    return (s * 999) if score_type == "score_sde" else (s.float() * N_SCALES).long().float()
+
+
+def vpode_tables(t_star, step_size=1e-3, score_type="score_sde"):
+    """Probability-flow ODE with torchdiffeq's fixed-grid Euler (runners/diffpure_ode.py:90-131,219-238):
+    time runs DOWN from t*/1000 to 1e-5 on the grid t_i = t0 - i*step (last point forced to t1);
+    dx/dt = -beta/2 x + beta/(2 sigma) eps, so x <- (1 - beta dt/2) x + beta dt/(2 sigma) eps with dt = t_{i+1} - t_i < 0."""
+    t0, t1 = t_star * 1. / 1000, 1e-5
+    ts = torch.linspace(t0, t1, 2)
+    niters = int(torch.ceil((ts[0] - ts[1]) / step_size + 1).item())          # torchdiffeq _grid_constructor_from_step_size
+    grid = ts[0] - torch.arange(0, niters, dtype=ts.dtype) * step_size
+    grid[-1] = ts[1]
+    s, dt = grid[:-1], grid[1:] - grid[:-1]
+    beta = BETA_MIN + s * (BETA_MAX - BETA_MIN)
+    sigma = _sigma(s, score_type)
+    coef = torch.stack([1 - 0.5 * beta * dt, 0.5 * (beta / sigma) * dt, torch.zeros_like(s)], 1)
+    return _cond(s, score_type).float().numpy().astype(np.float32), coef.float().numpy().astype(np.float32)
+
+
+def ldsde_tables(t_star, sigma2=1e-3, lambda_ld=1e-2, eta=5.0, score_type="score_sde", dt=1e-2):
+    """Langevin-dynamics SDE baseline (runners/diffpure_ldsde.py:92-148,196-200,229-243): torchsde Euler with dt = 1e-2 on
+    [1 - t*/1000, 1 - 1e-5]; the score is always evaluated at t = 1e-2;
+    f = -lambda/2 (eps/sigma + (x - x_init)/sigma2), g = sqrt(lambda) eta  ->  4 coefficients (x, eps, z, x_init)."""
+    t0, t1 = 1 - t_star * 1. / 1000, 1 - 1e-5
+    ts = torch.linspace(t0, t1, 2)
+    grid = [ts[0]]
+    while grid[-1] < ts[-1]:
+        grid.append(torch.minimum(grid[-1] + dt, ts[-1]))
+    grid = torch.stack(grid)
+    h = grid[1:] - grid[:-1]
+    tfix = torch.zeros_like(h) + 1e-2
+    sigma = _sigma(tfix, score_type)
+    c0 = 1 - 0.5 * lambda_ld * h / sigma2
+    c1 = -0.5 * lambda_ld * h / sigma
+    c2 = float(np.sqrt(lambda_ld) * eta) * torch.sqrt(h)
+    c3 = 0.5 * lambda_ld * h / sigma2
+    coef = torch.stack([c0, c1, c2, c3], 1)
+    return _cond(tfix, score_type).float().numpy().astype(np.float32), coef.float().numpy().astype(np.float32)

@@ -179,6 +179,7 @@ int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float*
 
 #define DP_UPDATE_LINEAR 0 /* x <- c[0]*x + c[1]*eps + c[2]*z                 (VP-SDE Euler-Maruyama; ddpm fixed-var) */
 #define DP_UPDATE_LEARNED_RANGE 1 /* guided_diffusion p_sample with learned-range variance and x0 clamp; 8 coefs */
+#define DP_UPDATE_LINEAR_ANCHORED 2 /* x <- c[0]*x + c[1]*eps + c[2]*z + c[3]*x_init  (Langevin-dynamics SDE, runners/diffpure_ldsde.py) */
 
 typedef struct {
   int steps;
@@ -192,6 +193,7 @@ typedef struct {
   const float* step_noise;  /* device [steps,B,3,H,W] standard normals or NULL -> counter-based generator */
   uint64_t seed;
   uint64_t sample_offset;   /* global index of sample 0 (multi-GPU sharding keeps streams identical) */
+  const float* anchor;      /* DP_UPDATE_LINEAR_ANCHORED: device [B,3,H,W] x_init, or NULL -> the (diffused) initial state */
 } dp_purify_params;
 
 /* The whole purification loop on the device: forward-diffuse, then `steps` x (UNet + fused update).

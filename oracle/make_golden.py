@@ -164,8 +164,39 @@ def golden_adm_and_celeba():
     print("celeba tiny |y|", y.abs().mean().item())
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--siblings" not in sys.argv:
     if "--adm-celeba" not in sys.argv:
         main()
     if "--ncsnpp" not in sys.argv:
         golden_adm_and_celeba()
+
+
+def golden_siblings():
+    """Reference VPODE.ode_fn (runners/diffpure_ode.py:90-125) and LDSDE.f/g (runners/diffpure_ldsde.py:92-148) on the
+    reduced DDPM++ (tinyB) -- pins oracle/sde.py:vpode_f / ldsde_f."""
+    torch.set_grad_enabled(False)
+    ref_import.install()
+    m, c = ref_import.build_ncsnpp(dict(nf=64, ch_mult=[1, 2, 2], num_res_blocks=1, attn_resolutions=[16],
+                                        **{"data.image_size": 32}))
+    cfg_o = O.tiny_cfg(64, (1, 2, 2), 1, (16,), 32)
+    sdt = weights.make_state_dict(O.param_shapes(cfg_o), seed=1)
+    m.load_state_dict(sdt, strict=False)
+    from runners.diffpure_ode import VPODE
+    from runners.diffpure_ldsde import LDSDE
+    g = torch.Generator().manual_seed(500)
+    x = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    x_init = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    t = torch.tensor(0.07)
+    ode = VPODE(model=m, score_type="score_sde", img_shape=(3, 32, 32))
+    dx = ode(t, (x.reshape(2, -1),))[0].reshape(2, 3, 32, 32)
+    ld = LDSDE(model=m, x_init=x_init.reshape(2, -1), score_type="score_sde", img_shape=(3, 32, 32), sigma2=1e-3,
+               lambda_ld=1e-2, eta=5)
+    f = ld.f(torch.tensor(0.95), x.reshape(2, -1)).reshape(2, 3, 32, 32)
+    gg = ld.g(torch.tensor(0.95), x.reshape(2, -1))[:, 0]
+    np.savez_compressed(os.path.join(OUT, "siblings_tinyB.npz"), x=x.numpy(), x_init=x_init.numpy(), t_ode=0.07,
+                        ode_dx=dx.numpy(), ld_f=f.numpy(), ld_g=gg.numpy(), seed=1)
+    print("siblings: |dx|", dx.abs().mean().item(), "|f|", f.abs().mean().item(), "g", gg)
+
+
+if __name__ == "__main__" and "--siblings" in sys.argv:
+    golden_siblings()

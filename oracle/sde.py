@@ -76,3 +76,74 @@ def purify_sde(unet, x0, t_star, init_noise, step_noise, score_type="score_sde",
 
 def num_steps(t_star):
     return len(time_grid(t_star)) - 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sibling loops (same UNet, different integrand): probability-flow ODE and Langevin-dynamics SDE
+# ---------------------------------------------------------------------------------------------------------
+def _score(unet, score_type, s, x_img):
+    """score at forward time s (vector [B]); shared by VPODE.ode_fn (diffpure_ode.py:90-125) and LDSDE.ldsde_fn."""
+    if score_type == "score_sde":
+        out = unet(x_img, s * 999)
+        std = torch.sqrt(1. - torch.exp(2. * (-0.25 * s ** 2 * (BETA_MAX - BETA_MIN) - 0.5 * s * BETA_MIN)))
+        return -out / std[:, None, None, None]
+    disc = (s.float() * N_SCALES).long()
+    out = unet(x_img, disc)[:, :3]
+    ac = torch.exp(-0.5 * (BETA_MAX - BETA_MIN) * s ** 2 - BETA_MIN * s)
+    return (-1. / torch.sqrt(1. - ac))[:, None, None, None] * out
+
+
+def vpode_f(unet, score_type, t, x_img):
+    """VPODE.ode_fn, diffpure_ode.py:90-125: drift - g^2/2 * score at forward time t."""
+    B = x_img.shape[0]
+    s = t.expand(B)
+    beta = BETA_MIN + s * (BETA_MAX - BETA_MIN)
+    return -0.5 * beta[:, None, None, None] * x_img - 0.5 * beta[:, None, None, None] * _score(unet, score_type, s, x_img)
+
+
+def purify_ode(unet, x0, t_star, init_noise, step_size=1e-3, score_type="score_sde"):
+    """OdeGuidedDiffusion.image_editing_sample with method='euler' (diffpure_ode.py:219-241); torchdiffeq's fixed-grid
+    Euler (third party, torchdiffeq==0.2.1, absent offline) restated: t_i = t0 - i*step, last point = t1, y += dt*f."""
+    x = forward_diffuse(x0, init_noise, t_star)
+    t0, t1 = t_star * 1. / 1000, 1e-5
+    ts = torch.linspace(t0, t1, 2)
+    niters = int(torch.ceil((ts[0] - ts[1]) / step_size + 1).item())
+    grid = ts[0] - torch.arange(0, niters, dtype=ts.dtype) * step_size
+    grid[-1] = ts[1]
+    for i in range(len(grid) - 1):
+        x = x + (grid[i + 1] - grid[i]) * vpode_f(unet, score_type, grid[i], x)
+    return x
+
+
+def ldsde_f(unet, score_type, x_img, x_init, sigma2, lambda_ld):
+    """LDSDE.ldsde_fn drift, diffpure_ldsde.py:92-131 (score always at t = 1e-2)."""
+    B = x_img.shape[0]
+    s = torch.zeros(B) + 1e-2
+    return -0.5 * (-_score(unet, score_type, s, x_img) + (x_img - x_init) / sigma2) * lambda_ld
+
+
+def purify_ldsde(unet, x0, t_star, step_noise, sigma2=1e-3, lambda_ld=1e-2, eta=5.0, score_type="score_sde", dt=1e-2):
+    """LDGuidedDiffusion.image_editing_sample (diffpure_ldsde.py:205-247): no forward diffusion, torchsde Euler, dt 1e-2."""
+    t0, t1 = 1 - t_star * 1. / 1000, 1 - 1e-5
+    ts = torch.linspace(t0, t1, 2)
+    t = ts[0]
+    x = x0
+    k = 0
+    g = float(np.sqrt(lambda_ld) * eta)
+    while t < ts[-1]:
+        tn = torch.minimum(t + dt, ts[-1])
+        h = tn - t
+        x = x + ldsde_f(unet, score_type, x, x0, sigma2, lambda_ld) * h + g * step_noise[k] * torch.sqrt(h)
+        t = tn
+        k += 1
+    return x
+
+
+def num_steps_ldsde(t_star, dt=1e-2):
+    t0, t1 = 1 - t_star * 1. / 1000, 1 - 1e-5
+    ts = torch.linspace(t0, t1, 2)
+    t, n = ts[0], 0
+    while t < ts[-1]:
+        t = torch.minimum(t + dt, ts[-1])
+        n += 1
+    return n
