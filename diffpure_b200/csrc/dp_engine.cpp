@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,11 +27,16 @@ struct StatsReduce {
   int B, P, C;
 };
 
+// CTA-pair GEMM tiles (see dp_op_gemm): 0 = off, 1 = BN 128 only, 2 = BN 128 and 256; the DP_GEMM_PAIR environment
+// variable overrides it for A/B runs
+constexpr int kDefaultPairMode = 2;
+
 struct Op {
   OpKind kind;
   dp::EmbedParams embed;
   dp::GemmParams gemm;
   int bn = 128;
+  int cg = 1;  // CTAs per tile
   bool softmax = false;
   dp::GnParams gn;
   dp_stats_desc stats;
@@ -128,7 +134,7 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       break;
     }
     case OP_GEMM:
-      rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s);
+      rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s, op.cg);
       break;
     case OP_GN:
       rc = dp::launch_gn_apply(op.gn, op.gn.stats0 ? e->gn_ss : nullptr, e->num_sms, s);
@@ -393,8 +399,6 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     ktotal += static_cast<long long>(a.taps) * a.C;
   }
   p.nseg = d->nseg;
-  if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, d->w_cols > 0 ? d->w_cols : ktotal, d->w_rows, d->w_pitch, bn, &err))
-    return fail(e, DP_ERR_CUDA, "gemm: B tensor map: " + err);
   p.a_batch_rows = d->a_batch_rows;
   p.b_batch_rows = d->b_batch_rows;
   p.out_batch_stride = d->out_batch_stride;
@@ -425,6 +429,24 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   p.rowsum_out = d->rowsum_out;
   if (op.softmax && (!p.out_bf16 || !p.rowsum_out)) return fail(e, DP_ERR_INVALID, "gemm softmax needs out_bf16 + rowsum_out");
   if (!op.softmax && !p.out_f32 && !p.out_bf16) return fail(e, DP_ERR_INVALID, "gemm: no output");
+  // CTA pairs (cta_group::2, 256 x BN tiles over two SMs) for the convolutions: less shared-memory operand traffic per
+  // SM. DP_GEMM_PAIR=0 disables, 1 = BN 128 only, 2 = BN 128 and 256 (measurement switch).
+  op.cg = 1;
+  {
+    const char* pm = std::getenv("DP_GEMM_PAIR");
+    const int mode = pm ? std::atoi(pm) : kDefaultPairMode;
+    const long long units = static_cast<long long>(p.m_tiles / 2) * p.n_tiles * p.batch;
+    // measured (tests/selftest_gemm perf): +8..27% on the 3x3 convolutions; a short-K tile with an fp32 residual is
+    // epilogue/HBM-bound and loses 4% to the pair's lock step, so it keeps single-CTA tiles
+    const bool epilogue_bound = p.resid != nullptr && ktotal < 2048;
+    if (mode > 0 && (bn == 128 || mode > 1) && ktotal >= 1024 && !epilogue_bound && units >= e->num_sms / 2 &&
+        dp::gemm_pair_supported(p, bn, op.softmax))
+      op.cg = 2;
+  }
+  p.num_stages = dp::gemm_max_stages(bn, op.cg);
+  if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, d->w_cols > 0 ? d->w_cols : ktotal, d->w_rows, d->w_pitch, bn / op.cg,
+                        &err))
+    return fail(e, DP_ERR_CUDA, "gemm: B tensor map: " + err);
   e->ops.push_back(op);
   return DP_OK;
 }

@@ -27,9 +27,11 @@ constexpr int kStgPitch = 36;  // floats; 144-byte rows keep float4 accesses ali
 
 constexpr int kMaxStages = 8;
 
-template <int BN>
+// CG = CTAs per tile: 1, or 2 = a CTA pair (cluster of two SMs of one TPC) working on a 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and BN/2 rows of B.
+template <int BN, int CG = 1>
 struct Smem {
-  static constexpr int kStageBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
   static constexpr int kStagingFloats = epi_warps(BN) * 32 * kStgPitch;
   static constexpr int kStatsFloats = 8 * BN * 2;
@@ -44,12 +46,14 @@ struct Tile {
   int bo, hd;  // outer batch entry, head
 };
 
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
+// t enumerates (batch, M unit, N tile); an M unit is `cg` consecutive 128-row tiles, CTA `rank` of the pair owns one
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t, int cg = 1, int rank = 0) {
   Tile c;
   c.nt = t % p.n_tiles;
   const int r = t / p.n_tiles;
-  c.mt = r % p.m_tiles;
-  c.b = r / p.m_tiles;
+  const int m_units = p.m_tiles / cg;
+  c.mt = (r % m_units) * cg + rank;
+  c.b = r / m_units;
   c.bo = c.b / p.inner;
   c.hd = c.b - c.bo * p.inner;
   if (p.imgs_per_tile > 1) {
@@ -73,9 +77,11 @@ __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + _
 constexpr int E_BIAS_N = 1, E_BIAS_M = 2, E_ROWVEC = 4, E_ROWSCALE = 8, E_RESID = 16, E_SILU = 32, E_F32 = 64,
               E_BF16 = 128, E_STATS = 256, E_ALPHA = 512, E_GENERIC = 1 << 14, E_SOFTMAX = 1 << 15;
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using L = Smem<BN>;
+  using L = Smem<BN, CG>;
+  static_assert(CG == 1 || CG == 2, "CTAs per tile");
+  static_assert(CG == 1 || (EPI & E_SOFTMAX) == 0, "the softmax epilogue is single-CTA");
   constexpr bool kSoftmax = (EPI & E_SOFTMAX) != 0;
   constexpr bool kGeneric = (EPI & E_GENERIC) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -111,19 +117,25 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * EW);
+      // pair: one arrival per epilogue warp of either CTA, all on the leader's barrier
+      mbar_init(tempty_bar(a), CG == 2 ? 2 * EW : 32 * EW);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), 2 * BN);
+    if constexpr (CG == 2) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_holder)), 2 * BN);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), 2 * BN);
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before any remote signal
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.batch;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int work0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_tiles = (p.m_tiles / CG) * p.n_tiles * p.batch;
   int num_kb = 0;
   for (int s = 0; s < p.nseg; ++s) num_kb += p.a[s].taps * p.a[s].kchunks;
 
@@ -132,10 +144,10 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const Tile c = decode_tile(p, t);
+      for (int t = work0; t < total_tiles; t += work_stride) {
+        const Tile c = decode_tile(p, t, CG, rank);
         int kglobal = 0;
-        const int brow = c.nt * BN + c.bo * p.b_batch_rows + c.hd * p.b_inner_rows;
+        const int brow = c.nt * BN + rank * (BN / CG) + c.bo * p.b_batch_rows + c.hd * p.b_inner_rows;
         const int a_k0 = c.hd * p.a_inner_k;
         const int b_k0 = c.hd * p.b_inner_k;
         for (int s = 0; s < p.nseg; ++s) {
@@ -147,10 +159,18 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
             const int c2 = c.h0 * seg.stride + ky - seg.pad;
             for (int kc = 0; kc < seg.kchunks; ++kc) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
               const uint32_t sa = base + stage * L::kStageBytes;
-              tma_load_4d(sa, &seg.tmap, full_bar(stage), a_k0 + kc * kBlockK, c1, c2, c.n0);
-              tma_load_2d(sa + kStageABytes, &p.tmap_b, full_bar(stage), b_k0 + kglobal, brow);
+              if constexpr (CG == 2) {
+                // both CTAs' bytes are counted on the leader's barrier (the MMA issuer waits there)
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+                const uint32_t sig = mapa_u32(full_bar(stage), 0);
+                tma_load_4d_pair(sa, &seg.tmap, sig, a_k0 + kc * kBlockK, c1, c2, c.n0);
+                tma_load_2d_pair(sa + kStageABytes, &p.tmap_b, sig, b_k0 + kglobal, brow);
+              } else {
+                mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+                tma_load_4d(sa, &seg.tmap, full_bar(stage), a_k0 + kc * kBlockK, c1, c2, c.n0);
+                tma_load_2d(sa + kStageABytes, &p.tmap_b, full_bar(stage), b_k0 + kglobal, brow);
+              }
               kglobal += kBlockK;
               if (++stage == stages) {
                 stage = 0;
@@ -161,13 +181,13 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = work0; t < total_tiles; t += work_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -183,10 +203,16 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(as));
+          if constexpr (CG == 2) {  // frees the stage / publishes the accumulator in both CTAs
+            umma_commit_pair(empty_bar(stage), 3);
+            if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as), 3);
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit(tfull_bar(as));
+          }
         }
         __syncwarp();
         if (++stage == stages) {
@@ -217,10 +243,10 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     const float alpha = p.alpha;
     const int ldc = static_cast<int>(p.ldc);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = work0; t < total_tiles; t += work_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const Tile c = decode_tile(p, t);
+      const Tile c = decode_tile(p, t, CG, rank);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       const int row0 = c.mt * kBlockM + q * 32;  // row within the batch entry
       const long long obase = static_cast<long long>(c.bo) * p.out_batch_stride +
@@ -342,7 +368,12 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
           if (bi == kBlocks - 1) {
             // this warp has read its share of the accumulator: hand the TMEM stage back to the MMA warp
             tc_fence_before_sync();
-            mbar_arrive(tempty_bar(as));
+            if constexpr (CG == 2) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));
+            } else {
+              mbar_arrive(tempty_bar(as));
+            }
           }
 #ifdef DP_EXP_NO_EPI
           if (r[0] == 0x12345678u) p.out_f32[0] = 1.f;  // keep the TMEM read alive, skip everything else
@@ -448,10 +479,12 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // no CTA of the pair may exit while its peer can still signal it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -461,9 +494,40 @@ int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (total <= 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
   const size_t smem = Smem<BN>::total(p.num_stages);
-  gemm_kernel<BN, EPI><<<grid, num_threads(BN), smem, stream>>>(p);
+  gemm_kernel<BN, EPI, 1><<<grid, num_threads(BN), smem, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
+
+// CTA-pair launch: clusters of two CTAs, one pair per TPC
+template <int BN, int EPI>
+int launch_pair_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
+  const int total = (p.m_tiles / 2) * p.n_tiles * p.batch;
+  if (total <= 0 || (p.m_tiles & 1)) return static_cast<int>(cudaErrorInvalidValue);
+  const int pairs = total < num_sms / 2 ? total : num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(num_threads(BN));
+  cfg.dynamicSmemBytes = Smem<BN, 2>::total(p.num_stages);
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, 2>, p));
+}
+
+// epilogues of the convolutions, the only ops big enough for CTA pairs
+#define DP_EPI_LIST_PAIR(X)                                     \
+  X(E_BIAS_N | E_ROWVEC | E_F32 | E_STATS)                      \
+  X(E_BIAS_N | E_ROWVEC | E_BF16 | E_STATS)                     \
+  X(E_BIAS_N | E_BF16 | E_STATS)                                \
+  X(E_BIAS_N | E_RESID | E_F32 | E_STATS | E_ALPHA)             \
+  X(E_BIAS_N | E_F32 | E_STATS | E_ALPHA)                       \
+  X(E_BIAS_N | E_RESID | E_F32 | E_STATS)                       \
+  X(E_BIAS_N | E_F32 | E_STATS)
 
 // epilogue specialisations (every lowering's common cases); others use E_GENERIC
 #define DP_EPI_LIST(X)                                          \
@@ -498,6 +562,23 @@ int epi_mask_of(const GemmParams& p) {
   return m;
 }
 
+bool pair_mask_ok(int mask) {
+#define X(M) \
+  if (mask == (M)) return true;
+  DP_EPI_LIST_PAIR(X)
+#undef X
+  return false;
+}
+
+template <int BN>
+int dispatch_pair(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
+#define X(M) \
+  if (mask == (M)) return launch_pair_t<BN, (M)>(p, num_sms, stream);
+  DP_EPI_LIST_PAIR(X)
+#undef X
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
 template <int BN>
 int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
 #define X(M) \
@@ -509,33 +590,47 @@ int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
-size_t gemm_smem_bytes(int bn, int stages) {
+size_t gemm_smem_bytes(int bn, int stages, int cg) {
+  if (cg == 2) return bn == 256 ? Smem<256, 2>::total(stages) : Smem<128, 2>::total(stages);
   return bn == 256 ? Smem<256>::total(stages) : (bn == 32 ? Smem<32>::total(stages) : Smem<128>::total(stages));
 }
 
-int gemm_max_stages(int bn) {
+int gemm_max_stages(int bn, int cg) {
   const size_t cap = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
   int s = kMaxStages;
-  while (s > 2 && gemm_smem_bytes(bn, s) > cap) --s;
+  while (s > 2 && gemm_smem_bytes(bn, s, cg) > cap) --s;
   return s;
+}
+
+bool gemm_pair_supported(const GemmParams& p, int bn, bool softmax) {
+  return !softmax && (bn == 128 || bn == 256) && (p.m_tiles % 2 == 0) && pair_mask_ok(epi_mask_of(p));
 }
 
 int gemm_init() {
   cudaError_t e;
 #define X(M)                                                                                       \
-  e = cudaFuncSetAttribute(gemm_kernel<128, (M)>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+  e = cudaFuncSetAttribute(gemm_kernel<128, (M), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                            static_cast<int>(Smem<128>::total(gemm_max_stages(128))));              \
   if (e != cudaSuccess) return static_cast<int>(e);                                                \
-  e = cudaFuncSetAttribute(gemm_kernel<256, (M)>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+  e = cudaFuncSetAttribute(gemm_kernel<256, (M), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                            static_cast<int>(Smem<256>::total(gemm_max_stages(256))));              \
   if (e != cudaSuccess) return static_cast<int>(e);
   DP_EPI_LIST(X)
 #undef X
+#define X(M)                                                                                          \
+  e = cudaFuncSetAttribute(gemm_kernel<128, (M), 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           static_cast<int>(Smem<128, 2>::total(gemm_max_stages(128, 2))));           \
+  if (e != cudaSuccess) return static_cast<int>(e);                                                   \
+  e = cudaFuncSetAttribute(gemm_kernel<256, (M), 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           static_cast<int>(Smem<256, 2>::total(gemm_max_stages(256, 2))));           \
+  if (e != cudaSuccess) return static_cast<int>(e);
+  DP_EPI_LIST_PAIR(X)
+#undef X
   // narrow-N tile (output conv, N <= 32): only the plain bias epilogue and the generic fallback
-  e = cudaFuncSetAttribute(gemm_kernel<32, E_BIAS_N | E_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_kernel<32, E_BIAS_N | E_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
   if (e != cudaSuccess) return static_cast<int>(e);
-  e = cudaFuncSetAttribute(gemm_kernel<32, E_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_kernel<32, E_GENERIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
   if (e != cudaSuccess) return static_cast<int>(e);
   return 0;
@@ -555,7 +650,7 @@ TileBox gemm_tile_box(int H, int W) {
   return t;
 }
 
-void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn) {
+void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn, int cg) {
   const TileBox t = gemm_tile_box(H, W);
   p.H = H;
   p.W = W;
@@ -581,11 +676,15 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn) {
   p.n_tiles = (N + bn - 1) / bn;
   if (p.batch <= 0) p.batch = 1;
   if (p.inner <= 0) p.inner = 1;
-  p.num_stages = gemm_max_stages(bn);
+  p.num_stages = gemm_max_stages(bn, cg);
 }
 
-int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream) {
+int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream, int cg) {
   const int mask = softmax ? E_SOFTMAX : epi_mask_of(p);
+  if (cg == 2) {
+    if (!gemm_pair_supported(p, bn, softmax)) return static_cast<int>(cudaErrorInvalidValue);
+    return bn == 256 ? dispatch_pair<256>(p, mask, num_sms, stream) : dispatch_pair<128>(p, mask, num_sms, stream);
+  }
   if (bn == 32) {
     if (mask == (E_BIAS_N | E_F32)) return launch_t<32, E_BIAS_N | E_F32>(p, num_sms, stream);
     return launch_t<32, E_GENERIC>(p, num_sms, stream);

@@ -74,10 +74,13 @@ struct GemmParams {
 
 // Launches the persistent kernel (grid = min(tiles, num_sms)). BN in {128, 256}.
 // Returns cudaError_t as int.
-int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream);
+// cg = 2: CTA pairs (clusters of 2, tcgen05 cta_group::2) on 256 x BN tiles; needs gemm_pair_supported(), a B tensor map
+// with BN/2-row boxes and geometry filled with the same cg.
+int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream, int cg = 1);
+bool gemm_pair_supported(const GemmParams& p, int bn, bool softmax);
 // Dynamic shared memory needed for (bn, stages); and the max stage count that fits.
-size_t gemm_smem_bytes(int bn, int stages);
-int gemm_max_stages(int bn);
+size_t gemm_smem_bytes(int bn, int stages, int cg = 1);
+int gemm_max_stages(int bn, int cg = 1);
 // One-time cudaFuncSetAttribute for all instantiations.
 int gemm_init();
 
@@ -88,6 +91,6 @@ struct TileBox {
 TileBox gemm_tile_box(int H, int W);
 // Fills H/W/bw/bh/tiles_*/imgs_per_tile/M/N/m_tiles/n_tiles/stat_nseg/num_stages for an output grid of
 // B images of H x W pixels (plain GEMM: B = 1, H = 1, W = rows) and N output columns.
-void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn);
+void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn, int cg = 1);
 
 }  // namespace dp

@@ -55,6 +55,7 @@ struct ConvCase {
   int stride;         // 1 or 2 (stride 2: pad right/bottom only, taps 9)
   bool bias, rowvec, resid, silu, stats, out_bf16;
   float alpha;
+  int cg;             // 0/1 = one CTA per tile, 2 = CTA pair (cta_group::2)
 };
 
 static int num_sms = 148;
@@ -93,7 +94,8 @@ static void run_conv(const ConvCase& cs) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.batch = 1;
-  dp::gemm_fill_geometry(p, B, H, W, N, cs.bn);
+  const int cg = cs.cg == 2 ? 2 : 1;
+  dp::gemm_fill_geometry(p, B, H, W, N, cs.bn, cg);
   const int nsegs_total = p.m_tiles * p.stat_nseg;
   CK(cudaMalloc(&d_stats, (size_t)nsegs_total * N * 2 * 4));
   CK(cudaMemset(d_stats, 0, (size_t)nsegs_total * N * 2 * 4));
@@ -121,7 +123,7 @@ static void run_conv(const ConvCase& cs) {
     p.a[1].pad = 0;
     p.nseg = 2;
   }
-  if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, cs.bn, &err)) {
+  if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, cs.bn / cg, &err)) {
     printf("[%s] tmap b: %s\n", cs.name, err.c_str());
     failures++;
     return;
@@ -135,13 +137,15 @@ static void run_conv(const ConvCase& cs) {
   p.resid = cs.resid ? d_resid : nullptr;
   p.alpha = cs.alpha;
   p.silu = cs.silu;
-  p.out_f32 = d_out;
+  // pair kernels exist for the lowerings' epilogues only: a bf16 case writes bf16 alone there
+  const bool f32_out = !(cg == 2 && cs.out_bf16);
+  p.out_f32 = f32_out ? d_out : nullptr;
   p.out_bf16 = cs.out_bf16 ? d_outb : nullptr;
   p.ldc = N;
   p.out_batch_stride = 0;
   p.stats = cs.stats ? d_stats : nullptr;
 
-  int e = dp::launch_gemm(p, cs.bn, false, num_sms, 0);
+  int e = dp::launch_gemm(p, cs.bn, false, num_sms, 0, cg);
   cudaError_t se = cudaDeviceSynchronize();
   if (e || se != cudaSuccess) {
     printf("[%s] launch/sync error %d / %s\n", cs.name, e, cudaGetErrorString(se));
@@ -186,7 +190,7 @@ static void run_conv(const ConvCase& cs) {
           if (cs.silu) v = v / (1.f + expf(-v));
           if (cs.resid) v += resid[row * N + n];
           v *= cs.alpha;
-          const double d = fabs((double)v - out[row * N + n]);
+          const double d = f32_out ? fabs((double)v - out[row * N + n]) : 0.0;
           if (d > maxerr) maxerr = d;
           if (fabs(v) > maxref) maxref = fabs(v);
           if (cs.out_bf16) {
@@ -296,7 +300,7 @@ static void run_attention(int Bt, int T, int C, int bn_s) {
 }
 
 // perf mode: time one conv shape (no host reference): selftest_gemm perf B H W C0 taps N resid
-static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, int bnforce) {
+static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, int bnforce, int cg) {
   const size_t M = (size_t)B * H * W;
   const int Kt = taps * C0;
   __nv_bfloat16 *d_a, *d_w;
@@ -310,27 +314,30 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
   memset(&p, 0, sizeof(p));
   p.batch = 1;
   int bn = bnforce ? bnforce : ((N % 256 == 0) ? 256 : 128);
-  dp::gemm_fill_geometry(p, B, H, W, N, bn);
+  dp::gemm_fill_geometry(p, B, H, W, N, bn, cg);
   CK(cudaMalloc(&d_stats, (size_t)p.m_tiles * p.stat_nseg * N * 8));
   const dp::TileBox tb = dp::gemm_tile_box(H, W);
   std::string err;
   if (dp::make_act_tmap(&p.a[0].tmap, d_a, C0, C0, W, H, B, tb.bw, tb.bh, tb.bn, 1, &err)) { printf("%s\n", err.c_str()); exit(1); }
   p.a[0].taps = taps; p.a[0].kchunks = C0 / 64; p.a[0].stride = 1; p.a[0].pad = taps == 9 ? 1 : 0; p.nseg = 1;
-  if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, bn, &err)) { printf("%s\n", err.c_str()); exit(1); }
+  if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, bn / cg, &err)) { printf("%s\n", err.c_str()); exit(1); }
   p.bias = d_bias; p.alpha = 1.f; p.out_f32 = d_out; p.ldc = N; p.stats = d_stats;
   int sh = 0; while ((1 << sh) < H * W) ++sh;
   if (resid) { p.resid = d_res; p.alpha = 0.70710678f; } else { p.rowvec = d_rowvec; p.rowvec_ld = N; p.rowvec_shift = sh; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 3; ++i) dp::launch_gemm(p, bn, false, num_sms, 0);
+  for (int i = 0; i < 3; ++i) {
+    int e = dp::launch_gemm(p, bn, false, num_sms, 0, cg);
+    if (e) { printf("launch failed: %d\n", e); exit(1); }
+  }
   CK(cudaDeviceSynchronize());
   const int iters = 20;
   cudaEventRecord(e0);
-  for (int i = 0; i < iters; ++i) dp::launch_gemm(p, bn, false, num_sms, 0);
+  for (int i = 0; i < iters; ++i) dp::launch_gemm(p, bn, false, num_sms, 0, cg);
   cudaEventRecord(e1);
   CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   const double fl = 2.0 * M * N * Kt;
-  printf("perf B%d %dx%d C%d taps%d N%d bn%d resid%d: %.1f us  %.1f TF/s\n", B, H, W, C0, taps, N, bn, resid, ms / iters * 1e3, fl / (ms / iters * 1e-3) / 1e12);
+  printf("perf B%d %dx%d C%d taps%d N%d bn%d cg%d resid%d: %.1f us  %.1f TF/s\n", B, H, W, C0, taps, N, bn, cg, resid, ms / iters * 1e3, fl / (ms / iters * 1e-3) / 1e12);
 }
 
 int main(int argc, char** argv) {
@@ -343,8 +350,10 @@ int main(int argc, char** argv) {
   int e = dp::gemm_init();
   if (e) { printf("gemm_init failed %d\n", e); return 2; }
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  const bool pair_only = argc > 1 && !strcmp(argv[1], "pair");
   if (argc > 8 && !strcmp(argv[1], "perf")) {
-    run_perf(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]), argc > 9 ? atoi(argv[9]) : 0);
+    run_perf(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]), argc > 9 ? atoi(argv[9]) : 0,
+             argc > 10 ? atoi(argv[10]) : 1);
     return 0;
   }
 
@@ -364,14 +373,24 @@ int main(int argc, char** argv) {
       {"conv3x3 s2 32->16 128",    2, 16, 16, 128, 9,  0, 128, 128, 2, true, false,false,false,true, false, 1.f},
       {"conv3x3 256x256 64->128",  1, 256,256, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f},
       {"conv3x3 s2 256->128 64",   1, 128,128, 64, 9,  0, 128, 128, 2, true, false,false,false,false,false, 1.f},
+      // CTA pairs (cta_group::2): 256 x BN tiles across two SMs
+      {"pair conv3x3 32x32 128->128",  2, 32, 32, 128, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f, 2},
+      {"pair conv3x3 32x32 resid",     4, 32, 32, 128, 9,  0, 128, 128, 1, true, false,true, false,true, false, 0.70710678f, 2},
+      {"pair conv3x3+1x1 32x32 bf16",  2, 32, 32, 128, 9, 256, 128, 128, 1, true, false,false,false,true, true, 1.f, 2},
+      {"pair conv3x3 16x16 256->256",  4, 16, 16, 256, 9,  0, 256, 256, 1, true, true, false,false,true, true,  1.f, 2},
+      {"pair conv3x3 8x8 256 bn128",   8, 8,  8,  256, 9,  0, 256, 128, 1, true, false,true, false,true, false, 0.70710678f, 2},
+      {"pair conv3x3 4x4 256->256",    32, 4, 4,  256, 9,  0, 256, 256, 1, true, false,true, false,true, false, 0.70710678f, 2},
+      {"pair conv3x3 s2 32->16 128",   2, 16, 16, 128, 9,  0, 128, 128, 2, true, false,false,false,true, false, 1.f, 2},
+      {"pair conv 64x64 many tiles",   20, 64, 64, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f, 2},
   };
   const int ncases = sizeof(cases) / sizeof(cases[0]);
   for (int i = 0; i < ncases; ++i) {
     if (quick && i >= 4) break;
+    if (pair_only && cases[i].cg != 2) continue;
     run_conv(cases[i]);
   }
-  run_attention(3, 256, 256, 256);
-  if (!quick) run_attention(2, 128, 512, 128);
+  if (!pair_only) run_attention(3, 256, 256, 256);
+  if (!quick && !pair_only) run_attention(2, 128, 512, 128);
   printf("selftest_gemm: %d failure(s)\n", failures);
   return failures ? 1 : 0;
 }
