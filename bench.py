@@ -193,7 +193,7 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    batch, sub = 16, 4
+    batch, sub = 16, 10                                        # each step: ~4 s of CPU work
     for i in range(args.warmup + args.steps):
         rate, dt, threads = cpu_reference_rate(batch, sub)
         if i >= args.warmup:
@@ -359,9 +359,9 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and args.config == "cifar10":
-        rate, dt, threads = cpu_reference_rate(16, 4)
+        rate, dt, threads = cpu_reference_rate(16, 30)         # ~10-15 s of CPU work
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"oracle CPU port of the reference loop, batch 16 (configs[0]), 4 of 100 Euler steps "
+               "sample": f"oracle CPU port of the reference loop, batch 16 (configs[0]), 30 of 100 Euler steps "
                          f"({dt:.1f} s), extrapolated linearly; threads = fastest of 8/16/32/64"}
 
     launches = args.steps * (nsteps * (eng.launches_per_eval + 1) + 2)

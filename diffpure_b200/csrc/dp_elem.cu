@@ -3,6 +3,7 @@
 // conv, the C->3|6 output conv fused with the per-step SDE / DDPM update, short-sequence attention, layout
 // conversion. All activations are NHWC; vector width is 8 channels (32 B fp32 in, 16 B bf16 out).
 #include "dp_elem.cuh"
+#include "dp_launch.cuh"
 
 #include <cstdio>
 
@@ -61,6 +62,7 @@ __host__ __device__ float dp_normal(unsigned long long seed, unsigned long long 
 // timestep embedding
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(EmbedParams p) {
+  pdl_entry();
   const int b = blockIdx.x;
   const int half = p.dim / 2;
   const float cond = p.cond_per_sample ? p.cond_per_sample[b] : p.tables.cond[*p.tables.step];
@@ -75,7 +77,7 @@ __global__ void embed_kernel(EmbedParams p) {
 }
 
 int launch_embed(const EmbedParams& p, cudaStream_t s) {
-  embed_kernel<<<p.B, 128, 0, s>>>(p);
+  (void)launch_k(embed_kernel, dim3(p.B), dim3(128), 0, s, 1, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -84,6 +86,7 @@ int launch_embed(const EmbedParams& p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // ss layout: [B][2][C] fp32 (scale[C] then shift[C]); y = x * scale + shift folds mean, rstd, gamma, beta and FiLM.
 __global__ void __launch_bounds__(256) gn_finalize_kernel(GnParams p, float* __restrict__ ss) {
+  pdl_entry();
   extern __shared__ float sm[];
   const int C = p.C0 + p.C1;
   const int G = p.groups;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnParams p, float* __r
 int launch_gn_finalize(const GnParams& p, float* ss, cudaStream_t s) {
   const int C = p.C0 + p.C1;
   const size_t smem = static_cast<size_t>(2 * C + 2 * p.groups) * sizeof(float);
-  gn_finalize_kernel<<<p.B, 256, smem, s>>>(p, ss);
+  (void)launch_k(gn_finalize_kernel, dim3(p.B), dim3(256), smem, s, 1, p, ss);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -157,6 +160,7 @@ int launch_gn_finalize(const GnParams& p, float* ss, cudaStream_t s) {
 // every thread owns one fixed 8-channel vector and issues all its loads before any compute / store.
 template <int RES, bool SRC16>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, const float* __restrict__ ss) {
+  pdl_entry();
   const int C = p.C0 + p.C1;
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -287,10 +291,10 @@ int launch_gn_apply(const GnParams& p, const float* ss, int num_sms, cudaStream_
   const size_t smem = 0;
   if (p.src0h != nullptr) {
     if (p.resample != 0 || p.C1 != 0) return static_cast<int>(cudaErrorInvalidValue);
-    gn_apply_kernel<0, true><<<grid, threads, smem, s>>>(p, ss);
-  } else if (p.resample == 0) gn_apply_kernel<0, false><<<grid, threads, smem, s>>>(p, ss);
-  else if (p.resample == 1) gn_apply_kernel<1, false><<<grid, threads, smem, s>>>(p, ss);
-  else gn_apply_kernel<2, false><<<grid, threads, smem, s>>>(p, ss);
+    (void)launch_k(gn_apply_kernel<0, true>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  } else if (p.resample == 0) (void)launch_k(gn_apply_kernel<0, false>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  else if (p.resample == 1) (void)launch_k(gn_apply_kernel<1, false>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  else (void)launch_k(gn_apply_kernel<2, false>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -298,6 +302,7 @@ int launch_gn_apply(const GnParams& p, const float* ss, int num_sms, cudaStream_
 // statistics
 // ------------------------------------------------------------------------------------------------
 __global__ void stats_kernel(const float* __restrict__ src, float* __restrict__ stats, int HW, int C, int P) {
+  pdl_entry();
   const int pp = blockIdx.x, b = blockIdx.y;
   const int r0 = pp * 128;
   const int r1 = min(HW, r0 + 128);
@@ -317,11 +322,12 @@ __global__ void stats_kernel(const float* __restrict__ src, float* __restrict__ 
 
 int launch_stats(const float* src, float* stats, int B, int HW, int C, cudaStream_t s) {
   const int P = (HW + 127) / 128;
-  stats_kernel<<<dim3(P, B), 256, 0, s>>>(src, stats, HW, C, P);
+  (void)launch_k(stats_kernel, dim3(P, B), dim3(256), 0, s, 1, src, stats, HW, C, P);
   return static_cast<int>(cudaGetLastError());
 }
 
 __global__ void stats_reduce_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int C2) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= C2) return;
@@ -332,7 +338,7 @@ __global__ void stats_reduce_kernel(const float* __restrict__ in, float* __restr
 
 int launch_stats_reduce(const float* in, float* out, int B, int P, int C, cudaStream_t s) {
   const int C2 = 2 * C;
-  stats_reduce_kernel<<<dim3((C2 + 255) / 256, B), 256, 0, s>>>(in, out, P, C2);
+  (void)launch_k(stats_reduce_kernel, dim3((C2 + 255) / 256, B), dim3(256), 0, s, 1, in, out, P, C2);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -342,6 +348,7 @@ int launch_stats_reduce(const float* in, float* out, int B, int P, int C, cudaSt
 // Each thread computes 4 consecutive pixels (along W) x 4 output channels: the 3 x 6 x 3 input patch lives in
 // registers and every 16-byte weight load from shared memory feeds 16 FMAs.
 __global__ void __launch_bounds__(256) conv_in_kernel(ConvInParams p) {
+  pdl_entry();
   extern __shared__ float sw[];  // [27][Cout] + bias[Cout]
   const int Cout = p.Cout;
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = p.w[i];
@@ -397,7 +404,7 @@ int launch_conv_in(const ConvInParams& p, cudaStream_t s) {
   const int gpb = 256 / vpp;
   const long long ngroups = static_cast<long long>(p.B) * p.H * (p.W / 4);
   const size_t smem = static_cast<size_t>(28 * p.Cout) * sizeof(float);
-  conv_in_kernel<<<static_cast<unsigned>((ngroups + gpb - 1) / gpb), 256, smem, s>>>(p);
+  (void)launch_k(conv_in_kernel, dim3(static_cast<unsigned>((ngroups + gpb - 1) / gpb)), dim3(256), smem, s, 1, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -408,6 +415,7 @@ constexpr int kConvOutPixPerWarp = 4;
 
 template <int CPL, int COUT>
 __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutParams p) {
+  pdl_entry();
   extern __shared__ float sw[];  // [9][CPL][COUT][32]
   const int C = p.C;
   for (int i = threadIdx.x; i < 9 * C * COUT; i += blockDim.x) {
@@ -519,7 +527,7 @@ static int launch_conv_out_t(const ConvOutParams& p, cudaStream_t s) {
   }
   const long long npix = static_cast<long long>(p.B) * p.H * p.W;
   const long long per_block = 8LL * kConvOutPixPerWarp;
-  conv_out_kernel<CPL, COUT><<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, smem, s>>>(p);
+  (void)launch_k(conv_out_kernel<CPL, COUT>, dim3(static_cast<unsigned>((npix + per_block - 1) / per_block)), dim3(256), smem, s, 1, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -541,6 +549,7 @@ int launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
 // per-step update from the output conv's result (fp32 [B*HW, ld], first Cout columns valid)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+  pdl_entry();
   const long long gp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int HW = p.H * p.W;
   const long long npix = static_cast<long long>(p.B) * HW;
@@ -588,7 +597,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
 
 int launch_update(const UpdateParams& p, cudaStream_t s) {
   const long long npix = static_cast<long long>(p.B) * p.H * p.W;
-  update_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, s>>>(p);
+  (void)launch_k(update_kernel, dim3(static_cast<unsigned>((npix + 255) / 256)), dim3(256), 0, s, 1, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -596,6 +605,7 @@ int launch_update(const UpdateParams& p, cudaStream_t s) {
 // short-sequence attention (T <= 64): one CTA per (head, sample), everything resident in smem
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_small_kernel(AttnSmallParams p) {
+  pdl_entry();
   extern __shared__ __align__(16) unsigned char smraw[];
   const int T = p.T, d = p.d;
   const int pitch = d + 2;  // bf16 elements; odd word pitch -> conflict-free row-strided reads
@@ -656,7 +666,7 @@ int launch_attn_small(const AttnSmallParams& p, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024));
   if (e != cudaSuccess) return static_cast<int>(e);
-  attn_small_kernel<<<dim3(p.heads, p.B), 256, smem, s>>>(p);
+  (void)launch_k(attn_small_kernel, dim3(p.heads, p.B), dim3(256), smem, s, 1, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -665,6 +675,7 @@ int launch_attn_small(const AttnSmallParams& p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ src,
                                                            __nv_bfloat16* __restrict__ out, long long rows, int T) {
+  pdl_entry();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -695,7 +706,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 int launch_softmax_rows(const float* src, __nv_bfloat16* out, long long rows, int T, cudaStream_t s) {
   if (T % 4) return static_cast<int>(cudaErrorInvalidValue);
-  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(src, out, rows, T);
+  (void)launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, 1, src, out, rows, T);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -705,6 +716,7 @@ int launch_softmax_rows(const float* src, __nv_bfloat16* out, long long rows, in
 __global__ void init_state_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                   float* __restrict__ x, int B, int C, int HW, float sx, float se,
                                   unsigned long long seed, unsigned long long sample_offset) {
+  pdl_entry();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(B) * C * HW;
   if (i >= n) return;
@@ -725,6 +737,7 @@ int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nh
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
+  pdl_entry();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(B) * C * HW;
   if (i >= n) return;
@@ -740,10 +753,11 @@ int launch_nhwc_to_nchw(const float* x_nhwc, float* out_nchw, int B, int C, int 
   return static_cast<int>(cudaGetLastError());
 }
 
-__global__ void step_advance_kernel(int* step) { *step += 1; }
+__global__ void step_advance_kernel(int* step) {
+  pdl_entry(); *step += 1; }
 
 int launch_step_advance(int* step, cudaStream_t s) {
-  step_advance_kernel<<<1, 1, 0, s>>>(step);
+  (void)launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, 1, step);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -359,6 +359,8 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   std::memset(&p, 0, sizeof(p));
   p.batch = d->batch > 0 ? d->batch : 1;
   op.softmax = d->softmax != 0;
+  long long kprobe = 0;
+  for (int sgi = 0; sgi < d->nseg; ++sgi) kprobe += static_cast<long long>(d->a[sgi].taps) * d->a[sgi].C;
   // tile width
   int bn = 128;
   if (op.softmax) {
@@ -366,7 +368,9 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     bn = d->N;
   } else if (d->N <= 32 && !d->stats) {
     bn = 32;  // narrow output (the C->3|6 conv padded to 8 columns): 128x32 tiles waste 4x instead of 16x of the MMA
-  } else if (d->N % 256 == 0) {
+  } else if (d->N % 256 == 0 && kprobe > 512) {
+    // (K <= 512: four to eight k-blocks per tile, the epilogue dominates and the 8-warp BN = 128 epilogue wins: measured
+    //  80 vs 90 us and 107 vs 159 us on the 16x16 attention projections, tests/selftest_gemm perf)
     dp::GemmParams probe;
     std::memset(&probe, 0, sizeof(probe));
     probe.batch = p.batch;

@@ -10,6 +10,7 @@
 //                               residual / scale / SiLU -> coalesced fp32|bf16 stores, plus deterministic
 //                               per-channel GroupNorm partial statistics of the tile; or row softmax.
 #include "dp_gemm.cuh"
+#include "dp_launch.cuh"
 #include "dp_ptx.cuh"
 
 #include <cstdio>
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global memory and overlaps the
+  // predecessor kernel's tail under programmatic dependent launch
+  pdl_entry();
 
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int work0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -494,8 +498,7 @@ int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (total <= 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
   const size_t smem = Smem<BN>::total(p.num_stages);
-  gemm_kernel<BN, EPI, 1><<<grid, num_threads(BN), smem, stream>>>(p);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 1>, dim3(grid), dim3(num_threads(BN)), smem, stream, 1, p));
 }
 
 // CTA-pair launch: clusters of two CTAs, one pair per TPC
@@ -504,19 +507,8 @@ int launch_pair_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   const int total = (p.m_tiles / 2) * p.n_tiles * p.batch;
   if (total <= 0 || (p.m_tiles & 1)) return static_cast<int>(cudaErrorInvalidValue);
   const int pairs = total < num_sms / 2 ? total : num_sms / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(num_threads(BN));
-  cfg.dynamicSmemBytes = Smem<BN, 2>::total(p.num_stages);
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, 2>, p));
+  return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 2>, dim3(2 * pairs), dim3(num_threads(BN)),
+                                   Smem<BN, 2>::total(p.num_stages), stream, 2, p));
 }
 
 // epilogues of the convolutions, the only ops big enough for CTA pairs
