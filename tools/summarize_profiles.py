@@ -32,8 +32,11 @@ def launch_list():
         agg[name][0] += 1
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
-    lines = [f"# ncu launch list ({tag}): python tests/gpu_profile_eval.py 512 2 (one DDPM++ UNet evaluation, B=512)",
-             f"# ncu --metrics gpu__time_duration.sum --clock-control none; per-launch device time, cold-cache/serialised:",
+    lines = [f"# ncu launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv python bench.py"
+             " --steps 1 --warmup 1 --no-cpu-baseline --no-e2e",
+             "# (the first 1200 launches of the bench command: the engine's eager warm-up of the forward and the step program,"
+             " i.e. two DDPM++ UNet evaluations at B=512, plus the start of the first purification)",
+             f"# per-launch device time, cold-cache/serialised:",
              f"# compare SHARES, not absolutes. unit of column 3: {unit}", "",
              f"{'kernel':70s} {'launches':>8s} {'total':>14s} {'share':>7s}"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -52,9 +55,10 @@ def gemm_capture(rep="prof_gemm.ncu-rep"):
             "l1tex__m_xbar2l1tex_read_bytes.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
             "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
-    lines = [f"# ncu --set full capture of the dominant kernel ({tag}): dp::gemm_kernel<BN, EPI> (tcgen05 implicit GEMM)",
-             "# launches: the first res-block convs of one DDPM++ evaluation at B=512: Conv_0 128->128 @32x32 (+temb, stats)",
-             "# and Conv_1 128->128 @32x32 (+residual, 1/sqrt2, stats)", ""]
+    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 3 -c 4 python tests/gpu_profile_eval.py 512 1  ({tag})",
+             "# dominant kernel dp::gemm_kernel<BN, EPI, CG> (tcgen05 implicit GEMM; CG = 2: CTA pair, cta_group::2).",
+             "# launches: the two res-blocks after the input conv of one DDPM++ evaluation at B=512: conv 128->128 @32x32 (+temb, stats,",
+             "# bf16 out; CTA pair) and conv 128->128 @32x32 (+fp32 residual, 1/sqrt2, stats; single CTA), twice", ""]
     traffic = []
     for ri, r in enumerate(rows[2:]):
         lines.append(f"## launch {ri}")
@@ -73,13 +77,14 @@ def gemm_capture(rep="prof_gemm.ncu-rep"):
     if traffic:
         json.dump({"dram_bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic),
                    "source": f"profiles/{tag}_gemm_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
-                   "algorithmic_bytes_per_launch_note": "conv 128->128 @32x32 B=512: A bf16 134 MB + out fp32 268 MB (+ residual fp32 268 MB)"},
+                   "algorithmic_bytes_per_launch_note": "B=512 conv 128->128 @32x32: temb/bf16-out launches 268 MB, fp32-residual launches 671 MB (A bf16 134 MB + residual 268 MB + out 268 MB)"},
                   open(os.path.join(out, "gemm_dram_bytes_per_launch.json"), "w"), indent=1)
     print("\n".join(lines[:24]))
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "diffpure_b200", "libdiffpure_b200.so")],
                           capture_output=True, text=True).stdout
     cnt = collections.Counter()
-    for m in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS.ARRIVE.TRANS64", "HMMA"):
+    for m in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.4D.2CTA", "LDTM", "UTCBAR", "UTCBAR.2CTA.MULTICAST", "SYNCS.ARRIVE.TRANS64",
+              "HMMA"):
         cnt[m] = sass.count(m)
     cnt["HMMA"] -= cnt["UTCHMMA"]   # "UTCHMMA" contains "HMMA": legacy mma.sync count is what is left
     open(os.path.join(out, f"{tag}_sass_mnemonics.txt"), "w").write(
