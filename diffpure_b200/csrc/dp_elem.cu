@@ -96,6 +96,22 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnParams p, float* __r
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int HW = p.H * p.W;
+  // affine / FiLM parameters do not depend on the statistics: fetch them first so their latency overlaps the partial sums
+  // (C <= 2 * blockDim.x for every UNet here; further channels are fetched in the last loop)
+  float pg[2], pb[2], pfs[2], pfb[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * 256;
+    pg[i] = pb[i] = pfs[i] = pfb[i] = 0.f;
+    if (c < C) {
+      pg[i] = __ldg(p.gamma + c);
+      pb[i] = __ldg(p.beta + c);
+      if (p.film) {
+        pfs[i] = __ldg(p.film + static_cast<size_t>(b) * p.film_ld + c);
+        pfb[i] = __ldg(p.film + static_cast<size_t>(b) * p.film_ld + C + c);
+      }
+    }
+  }
   for (int c = tid; c < C; c += blockDim.x) {
     const float* st;
     int P, Cx, cl;
@@ -104,7 +120,14 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnParams p, float* __r
     const float2* s2 = reinterpret_cast<const float2*>(st) + (static_cast<size_t>(b) * P * Cx + cl);
     float s = 0.f, q = 0.f;
     int pp = 0;
-    for (; pp + 4 <= P; pp += 4) {  // four independent loads in flight, summed in a fixed order
+    for (; pp + 8 <= P; pp += 8) {  // eight independent loads in flight, summed in a fixed order
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(s2 + static_cast<size_t>(pp + u) * Cx);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += v[u].x; q += v[u].y; }
+    }
+    for (; pp + 4 <= P; pp += 4) {
       const float2 v0 = __ldg(s2 + static_cast<size_t>(pp) * Cx), v1 = __ldg(s2 + static_cast<size_t>(pp + 1) * Cx);
       const float2 v2 = __ldg(s2 + static_cast<size_t>(pp + 2) * Cx), v3 = __ldg(s2 + static_cast<size_t>(pp + 3) * Cx);
       s += v0.x; q += v0.y; s += v1.x; q += v1.y; s += v2.x; q += v2.y; s += v3.x; q += v3.y;
@@ -133,15 +156,20 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnParams p, float* __r
     gs[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
   }
   __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
+  for (int c = tid, i = 0; c < C; c += blockDim.x, ++i) {
     const int g = c / cpg;
-    float a = p.gamma[c] * gs[2 * g + 1];
-    float bb = p.beta[c] - gs[2 * g] * a;
+    float gam, bet, fsv = 0.f, fbv = 0.f;
+    if (i < 2) { gam = pg[i]; bet = pb[i]; fsv = pfs[i]; fbv = pfb[i]; }
+    else {
+      gam = p.gamma[c]; bet = p.beta[c];
+      if (p.film) { fsv = p.film[static_cast<size_t>(b) * p.film_ld + c]; fbv = p.film[static_cast<size_t>(b) * p.film_ld + C + c]; }
+    }
+    float a = gam * gs[2 * g + 1];
+    float bb = bet - gs[2 * g] * a;
     if (p.film) {
-      const float fs = 1.0f + p.film[static_cast<size_t>(b) * p.film_ld + c];
-      const float fb = p.film[static_cast<size_t>(b) * p.film_ld + C + c];
+      const float fs = 1.0f + fsv;
       a *= fs;
-      bb = bb * fs + fb;
+      bb = bb * fs + fbv;
     }
     ss[(static_cast<size_t>(b) * 2) * C + c] = a;
     ss[(static_cast<size_t>(b) * 2 + 1) * C + c] = bb;

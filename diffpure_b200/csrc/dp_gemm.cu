@@ -332,21 +332,20 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
         // accumulator is even ready), so HBM latency overlaps the MMAs / the previous block instead of being
         // exposed once per block. `resid` and `out` may alias for the compiler, hence explicit register staging.
         struct Pre {
-          float4 add_lo, add_hi;
-          float4 rs[8];
+          float4 bias, rv_lo, rv_hi;  // kept raw: they are combined after the accumulator load, so the loads' latency
+          float4 rs[8];               // overlaps the tfull wait / tcgen05.ld instead of stalling in front of them
         };
         auto prefetch = [&](Pre& f, int ch) {
           const int cc = ch * 32 + c4;
           const bool ok = c.nt * BN + cc < p.N;
-          f.add_lo = make_float4(0.f, 0.f, 0.f, 0.f);
-          f.add_hi = f.add_lo;
+          f.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          f.rv_lo = f.bias;
+          f.rv_hi = f.bias;
           if (ok) {
-            if (has_bias_n) f.add_lo = f.add_hi = __ldg(reinterpret_cast<const float4*>(p.bias + c.nt * BN + cc));
+            if (has_bias_n) f.bias = __ldg(reinterpret_cast<const float4*>(p.bias + c.nt * BN + cc));
             if (has_rowvec) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(rv_lo + cc));
-              const float4 b = __ldg(reinterpret_cast<const float4*>(rv_hi + cc));
-              f.add_lo.x += a.x; f.add_lo.y += a.y; f.add_lo.z += a.z; f.add_lo.w += a.w;
-              f.add_hi.x += b.x; f.add_hi.y += b.y; f.add_hi.z += b.z; f.add_hi.w += b.w;
+              f.rv_lo = __ldg(reinterpret_cast<const float4*>(rv_lo + cc));
+              f.rv_hi = __ldg(reinterpret_cast<const float4*>(rv_hi + cc));
             }
           }
           if (has_resid) {
@@ -391,6 +390,11 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
           __syncwarp();
           const int cc = ch * 32 + c4;  // column inside the tile
           const bool colok = c.nt * BN + cc < p.N;
+          float4 add_lo = cur.bias, add_hi = cur.bias;
+          if (has_rowvec) {
+            add_lo.x += cur.rv_lo.x; add_lo.y += cur.rv_lo.y; add_lo.z += cur.rv_lo.z; add_lo.w += cur.rv_lo.w;
+            add_hi.x += cur.rv_hi.x; add_hi.y += cur.rv_hi.y; add_hi.z += cur.rv_hi.z; add_hi.w += cur.rv_hi.w;
+          }
           float st[16];  // [half][sum|sumsq][4 cols]
 #pragma unroll
           for (int i = 0; i < 16; ++i) st[i] = 0.f;
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
                 const float rinv = 1.0f / p.rowscale[static_cast<long long>(c.b) * p.M + row0 + rr];
                 v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv;
               }
-              const float4 ad = i8 < 4 ? cur.add_lo : cur.add_hi;
+              const float4 ad = i8 < 4 ? add_lo : add_hi;
               v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
               if (has_bias_m) {
                 const float bm = p.bias[row0 + rr];

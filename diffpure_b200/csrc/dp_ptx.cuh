@@ -176,8 +176,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive. Deliberately WITHOUT .release.cluster: that form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the
+// arrive (ncu source view: 14% of the pair kernel's stall samples, on the epilogue's critical path), i.e. it drains every
+// outstanding global store of the thread. The only data the barrier orders here is TMEM (tcgen05.ld results), which the
+// tcgen05.fence::before_thread_sync / after_thread_sync pair around the arrive / wait covers.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the executing CTA, completion bytes are signalled on `bar`, a
 // shared::cluster address that may live in the peer (leader) CTA.

@@ -322,6 +322,7 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
   p.a[0].taps = taps; p.a[0].kchunks = C0 / 64; p.a[0].stride = 1; p.a[0].pad = taps == 9 ? 1 : 0; p.nseg = 1;
   if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, bn / cg, &err)) { printf("%s\n", err.c_str()); exit(1); }
   p.bias = d_bias; p.alpha = 1.f; p.out_f32 = d_out; p.ldc = N; p.stats = d_stats;
+  if (getenv("DP_PERF_BF16")) { p.out_f32 = nullptr; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d_out); }  // bf16 output epilogue
   int sh = 0; while ((1 << sh) < H * W) ++sh;
   if (resid) { p.resid = d_res; p.alpha = 0.70710678f; } else { p.rowvec = d_rowvec; p.rowvec_ld = N; p.rowvec_shift = sh; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
