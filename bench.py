@@ -350,6 +350,7 @@ def main():
                 "traffic": None, "peak_source": peak_src, "launches_per_eval": gemm_n,
                 "avg_launch_ms": gemm_ms / gemm_n, "alg_flops_per_launch": alg_flops_eval / gemm_n,
                 "executed_gemm_flops_per_eval": gemm_fl, "kernel_share_of_eval": gemm_ms / eval_ms,
+                "cta_pair_launches_per_eval": eng.pair_gemms,
                 "eval_ms_by_kind": {k: round(v[1], 4) for k, v in by_kind.items()},
                 "whole_loop_frac_of_peak": (value / world) * nsteps * wl["flops"] / 1e12 / peak_tf}
     traffic_path = os.path.join(ROOT, "profiles", "gemm_dram_bytes_per_launch.json")

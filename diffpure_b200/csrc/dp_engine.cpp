@@ -293,6 +293,13 @@ size_t dp_bytes_allocated(const dp_engine* e) { return e ? e->total_bytes : 0; }
 int dp_program_size(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
 int dp_launches_per_eval(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
 
+int dp_gemm_pair_count(const dp_engine* e) {
+  int n = 0;
+  if (e)
+    for (const Op& op : e->ops) n += (op.kind == OP_GEMM && op.cg == 2) ? 1 : 0;
+  return n;
+}
+
 int dp_buffer_alloc(dp_engine* e, size_t bytes, int* buf_id) {
   if (!e || !buf_id) return DP_ERR_INVALID;
   DP_CUDA(e, cudaSetDevice(e->device));

@@ -181,6 +181,11 @@ class Engine:
     def launches_per_eval(self):
         return self.lib.dp_launches_per_eval(self.h)
 
+    @property
+    def pair_gemms(self):
+        """GEMM ops that run on CTA-pair (cta_group::2) tiles."""
+        return self.lib.dp_gemm_pair_count(self.h)
+
     def _dev(self):
         return torch.device("cuda", self.device)
 

@@ -103,6 +103,7 @@ SYMBOLS = {
     "dp_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dp_purify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PurifyParams), C.c_void_p]),
     "dp_launches_per_eval": (C.c_int, [C.c_void_p]),
+    "dp_gemm_pair_count": (C.c_int, [C.c_void_p]),
     "dp_profile_ops": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                  C.POINTER(C.c_double), C.c_int]),
     "dp_normal_host": (C.c_float, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),

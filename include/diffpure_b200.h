@@ -212,6 +212,9 @@ float dp_normal_host(uint64_t seed, uint64_t sample, uint32_t stream, uint32_t p
 /* Number of kernels one UNet evaluation launches (for bench accounting). */
 int dp_launches_per_eval(const dp_engine* e);
 
+/* How many of the program's GEMM ops run on CTA-pair (tcgen05 cta_group::2) tiles (tests / reporting). */
+int dp_gemm_pair_count(const dp_engine* e);
+
 #ifdef __cplusplus
 }
 #endif

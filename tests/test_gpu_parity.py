@@ -103,6 +103,30 @@ def test_full_model_trajectory_vs_oracle():
     assert rel(out, x) < TOL_TRAJ, rel(out, x)
 
 
+def test_pair_tiles_in_the_full_model_match_single_cta_tiles_and_oracle():
+    """At B=96 the 32x32 and 16x16 convolutions of the CIFAR-10 model run on CTA-pair (cta_group::2) tiles, at B=2 on
+    single-CTA tiles: the first two samples must agree with the B=2 engine and with the oracle."""
+    cfg = O.CIFAR10_CFG
+    sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
+    g = torch.Generator().manual_seed(15)
+    x = torch.rand(96, 3, 32, 32, generator=g) * 2 - 1
+    labels = torch.full((96,), 37.0)
+    with torch.no_grad():
+        y = O.forward(cfg, sd, x[:2], labels[:2])
+    e96 = engine_for(cfg, sd, 96)
+    y96 = e96.unet_forward(x.cuda(), labels.cuda()).cpu()
+    n96 = e96.pair_gemms
+    e96.close()
+    e2 = engine_for(cfg, sd, 2)
+    y2 = e2.unet_forward(x[:2].cuda(), labels[:2].cuda()).cpu()
+    n2 = e2.pair_gemms
+    e2.close()
+    assert n96 >= 40 and n2 == 0, (n96, n2)
+    assert rel(y96[:2], y) < TOL_EVAL, rel(y96[:2], y)
+    assert rel(y96[:2], y2) < 1e-3, rel(y96[:2], y2)      # same arithmetic, different tiling
+    assert torch.isfinite(y96).all()
+
+
 def test_determinism_and_shard_invariance():
     """Counter-based noise keyed by the global sample index: a batch of 8 equals two shards of 4 bit for bit,
     and repeated runs are bit-identical (no atomics anywhere on the path)."""
