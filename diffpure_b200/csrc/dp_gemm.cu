@@ -358,6 +358,17 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
           }
         };
         constexpr int kBlocks = BN / 32 / (EW / 4);  // 32-column blocks per epilogue warp
+        // attention row sums (P V product): the same 8 rows for every column block of the tile, fetched once and before
+        // the accumulator wait (they were a per-row dependent global load inside the block loop: 1/3 of the P V
+        // kernel's stall samples)
+        float rinv[8];
+        if (has_rowscale) {
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rr = i8 * 4 + rsub;
+            rinv[i8] = rr < rows_valid ? __ldg(p.rowscale + static_cast<long long>(c.b) * p.M + row0 + rr) : 1.0f;
+          }
+        }
         Pre cur, nxt;
         prefetch(cur, eh);
         mbar_wait(tfull_bar(as), aphase);
@@ -398,14 +409,18 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
           float st[16];  // [half][sum|sumsq][4 cols]
 #pragma unroll
           for (int i = 0; i < 16; ++i) st[i] = 0.f;
+          float4 vv[8];  // all eight 128-bit shared loads of the block issued back to back (they were serialised behind
+#pragma unroll       // one another's consumers through a reused register quad)
+          for (int i8 = 0; i8 < 8; ++i8)
+            vv[i8] = *reinterpret_cast<const float4*>(stg + (i8 * 4 + rsub) * kStgPitch + c4);
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int rr = i8 * 4 + rsub;
-            float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgPitch + c4);
+            float4 v = vv[i8];
             if (rr < rows_valid && colok) {
               if (has_rowscale) {
-                const float rinv = 1.0f / p.rowscale[static_cast<long long>(c.b) * p.M + row0 + rr];
-                v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv;
+                const float ri = 1.0f / rinv[i8];
+                v.x *= ri; v.y *= ri; v.z *= ri; v.w *= ri;
               }
               const float4 ad = i8 < 4 ? add_lo : add_hi;
               v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
