@@ -345,7 +345,7 @@ def main():
     eval_ms = sum(v[1] for v in by_kind.values())
     alg_flops_eval = wl["flops"] * B
     achieved_tf = alg_flops_eval / (gemm_ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "dp::gemm_kernel<BN,softmax> (tcgen05 implicit GEMM)",
+    roofline = {"bound": "tensor", "kernel": "dp::gemm_kernel<BN, EPI, CG> (tcgen05 implicit GEMM, CG=2: cta_group::2 CTA pairs)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "traffic": None, "peak_source": peak_src, "launches_per_eval": gemm_n,
                 "avg_launch_ms": gemm_ms / gemm_n, "alg_flops_per_launch": alg_flops_eval / gemm_n,

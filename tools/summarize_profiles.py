@@ -58,7 +58,7 @@ def gemm_capture(rep="prof_gemm.ncu-rep"):
     lines = [f"# ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 3 -c 4 python tests/gpu_profile_eval.py 512 1  ({tag})",
              "# dominant kernel dp::gemm_kernel<BN, EPI, CG> (tcgen05 implicit GEMM; CG = 2: CTA pair, cta_group::2).",
              "# launches: the two res-blocks after the input conv of one DDPM++ evaluation at B=512: conv 128->128 @32x32 (+temb, stats,",
-             "# bf16 out; CTA pair) and conv 128->128 @32x32 (+fp32 residual, 1/sqrt2, stats; single CTA), twice", ""]
+             "# bf16 out) and conv 128->128 @32x32 (+fp32 residual, 1/sqrt2, stats), twice -- all four on CTA pairs", ""]
     traffic = []
     for ri, r in enumerate(rows[2:]):
         lines.append(f"## launch {ri}")
