@@ -30,6 +30,9 @@ struct StatsReduce {
 // CTA-pair GEMM tiles (see dp_op_gemm): 0 = off, 1 = BN 128 only, 2 = BN 128 and 256; the DP_GEMM_PAIR environment
 // variable overrides it for A/B runs
 constexpr int kDefaultPairMode = 2;
+// fewer pair tiles than this leave most SMs idle either way; 32 admits the 4x4 level of the B=512 CIFAR-10 model
+// (64 pair tiles, one per CTA pair: measured 0.91 vs 1.01 ms per evaluation for its 40 convolutions)
+constexpr long long kMinPairTiles = 32;
 
 struct Op {
   OpKind kind;
@@ -449,7 +452,8 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     const long long units = static_cast<long long>(p.m_tiles / 2) * p.n_tiles * p.batch;
     // measured (tests/selftest_gemm perf, B=512): 32x32 128->128 1102 vs 952 TF/s, 256->128 1380 vs 1084, with fp32 residual
     // 991 vs 911, 16x16 512->256 1843 vs 1652
-    if (mode > 0 && (bn == 128 || mode > 1) && ktotal >= 1024 && units >= e->num_sms / 2 &&
+    // (small grids too: a lone tile per CTA is L2->SM bandwidth bound and a pair CTA loads 25% fewer operand bytes)
+    if (mode > 0 && (bn == 128 || mode > 1) && ktotal >= 1024 && units >= kMinPairTiles &&
         dp::gemm_pair_supported(p, bn, op.softmax))
       op.cg = 2;
   }

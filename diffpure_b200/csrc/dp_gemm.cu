@@ -265,52 +265,54 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
           mbar_arrive(tempty_bar(as));
           continue;
         }
+        // One thread = one TMEM lane = one whole output row. Two 32-column chunks are loaded per tcgen05.wait::ld (the
+        // wait covers every outstanding load, so pairing halves the exposed TMEM latency), and P is stored straight from
+        // this row-per-thread layout: 8 bf16 = one 16-byte store, four of them fill two whole 32-byte sectors.
+        static_assert((BN / 32) % 2 == 0, "softmax epilogue walks the row in pairs of 32-column chunks");
+        uint32_t r2[32];
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = 0; ch < BN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + ch * 32, r);
+          tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, r2);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
         }
         const float sc = p.softmax_scale * 1.4426950408889634f;
         float sum = 0.f;
+        const int row = row0 + lane;
+        const bool rowok = row < p.M;
+        __nv_bfloat16* const orow = p.out_bf16 + obase + static_cast<long long>(row) * p.ldc + c.nt * BN;
+        auto emit = [&](const uint32_t* rr, int ch) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float e0 = exp2f((__uint_as_float(rr[8 * j8 + 2 * u]) - mx) * sc);
+              const float e1 = exp2f((__uint_as_float(rr[8 * j8 + 2 * u + 1]) - mx) * sc);
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
+              sum += __low2float(b2);  // the row sum is taken over the rounded values the P V product will read
+              sum += __high2float(b2);
+              pk[u] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+            const int col = ch * 32 + j8 * 8;
+            if (rowok && c.nt * BN + col < p.N)
+              *reinterpret_cast<uint4*>(orow + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        };
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = 0; ch < BN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + ch * 32, r);
+          tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, r2);
           tmem_ld_wait();
-          if (ch == BN / 32 - 1) {
+          if (ch + 2 >= BN / 32) {
             tc_fence_before_sync();
             mbar_arrive(tempty_bar(as));
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 e4;
-            float* e = reinterpret_cast<float*>(&e4);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float ev = exp2f((__uint_as_float(r[4 * j + u]) - mx) * sc);
-              e[u] = __bfloat162float(__float2bfloat16_rn(ev));
-              sum += e[u];
-            }
-            *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * j) = e4;
-          }
-          __syncwarp();
-          const int col = c.nt * BN + ch * 32 + c4;
-#pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int rr = i8 * 4 + rsub;
-            const int row = row0 + rr;
-            const float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgPitch + c4);
-            if (row < p.M && col < p.N) {
-              __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(p.out_bf16 + obase + static_cast<long long>(row) * p.ldc + col) = pk;
-            }
-          }
-          __syncwarp();
+          emit(r, ch);
+          emit(r2, ch + 1);
         }
         if (row0 + lane < p.M) p.rowsum_out[static_cast<long long>(c.b) * p.M + row0 + lane] = sum;
       } else {
