@@ -138,7 +138,7 @@ static void run_conv(const ConvCase& cs) {
   p.alpha = cs.alpha;
   p.silu = cs.silu;
   // pair kernels exist for the lowerings' epilogues only: a bf16 case writes bf16 alone there
-  const bool f32_out = !(cg == 2 && cs.out_bf16);
+  const bool f32_out = !((cg == 2 || !strncmp(cs.name, "bf16only", 8)) && cs.out_bf16);
   p.out_f32 = f32_out ? d_out : nullptr;
   p.out_bf16 = cs.out_bf16 ? d_outb : nullptr;
   p.ldc = N;
@@ -374,6 +374,10 @@ int main(int argc, char** argv) {
       {"conv3x3 s2 32->16 128",    2, 16, 16, 128, 9,  0, 128, 128, 2, true, false,false,false,true, false, 1.f},
       {"conv3x3 256x256 64->128",  1, 256,256, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f},
       {"conv3x3 s2 256->128 64",   1, 128,128, 64, 9,  0, 128, 128, 2, true, false,false,false,false,false, 1.f},
+      // bf16-only outputs: the row-per-thread epilogue without the shared-memory transpose
+      {"bf16only gemm 300x256x512",    1, 1, 300, 512, 1,  0, 256, 128, 1, true, false,false,false,false,true,  1.f},
+      {"bf16only gemm 300x264 silu",   1, 1, 300, 128, 1,  0, 264, 128, 1, true, false,false,true, false,true,  1.f},
+      {"bf16only conv3x3 bn256",       3, 16, 16, 64, 9,  0, 256, 256, 1, false,false,false,false,false,true,  1.f},
       // CTA pairs (cta_group::2): 256 x BN tiles across two SMs
       {"pair conv3x3 32x32 128->128",  2, 32, 32, 128, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f, 2},
       {"pair conv3x3 32x32 resid",     4, 32, 32, 128, 9,  0, 128, 128, 1, true, false,true, false,true, false, 0.70710678f, 2},
