@@ -2,6 +2,8 @@
 // resample, concat) producing the bf16 GEMM operands, GroupNorm statistics, timestep embedding, the 3->C input
 // conv, the C->3|6 output conv fused with the per-step SDE / DDPM update, short-sequence attention, layout
 // conversion. All activations are NHWC; vector width is 8 channels (32 B fp32 in, 16 B bf16 out).
+#include <cstdlib>
+
 #include "dp_elem.cuh"
 #include "dp_launch.cuh"
 
@@ -186,7 +188,7 @@ int launch_gn_finalize(const GnParams& p, float* ss, cudaStream_t s) {
 // Streaming apply: plain large grid (measured 5.9-6.1 TB/s for this access shape vs 3.7 TB/s for a persistent loop,
 // tools/bench_stream.cu). One CTA = U*rpi output pixels of one sample; scale/shift of the sample staged in smem;
 // every thread owns one fixed 8-channel vector and issues all its loads before any compute / store.
-template <int RES, bool SRC16>
+template <int RES, bool SRC16, int U>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, const float* __restrict__ ss) {
   pdl_entry();
   const int C = p.C0 + p.C1;
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, const float* 
   const int rpi = blockDim.x / vpp;
   const int c = (tid % vpp) * 8;
   const int pr = tid / vpp;
-  constexpr int U = RES == 2 ? 1 : 2;
+  static_assert(RES != 2 || U == 1, "the 2x2-mean variant handles one output pixel per thread");
   constexpr int LD = RES == 2 ? 8 : 2;  // float4 loads per output pixel
   const float* src;
   int Cx;
@@ -314,15 +316,22 @@ int launch_gn_apply(const GnParams& p, const float* ss, int num_sms, cudaStream_
   const int Ho = p.resample == 1 ? p.H * 2 : (p.resample == 2 ? p.H / 2 : p.H);
   const int Wo = p.resample == 1 ? p.W * 2 : (p.resample == 2 ? p.W / 2 : p.W);
   const int HWo = Ho * Wo;
-  const int U = p.resample == 2 ? 1 : 2;
+  // pixels per thread: 4 on the large un-resampled tensors (more 16-byte loads in flight per thread; measured per DDPM++
+  // evaluation at B=512 on one box: 7.59 ms with 2, 6.70-6.81 ms with 4, 7.62 ms with 8; DP_GN_U=2 restores 2),
+  // 2 otherwise, 1 for the 2x2-mean variant (8 loads per output pixel already)
+  static const int u_big = [] { const char* v = std::getenv("DP_GN_U"); return v ? std::atoi(v) : 4; }();
+  const int U = p.resample == 2 ? 1 : ((p.resample == 0 && HWo >= 256 && u_big >= 4) ? 4 : 2);
   const dim3 grid((HWo + U * rpi - 1) / (U * rpi), p.B);
   const size_t smem = 0;
   if (p.src0h != nullptr) {
     if (p.resample != 0 || p.C1 != 0) return static_cast<int>(cudaErrorInvalidValue);
-    (void)launch_k(gn_apply_kernel<0, true>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
-  } else if (p.resample == 0) (void)launch_k(gn_apply_kernel<0, false>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
-  else if (p.resample == 1) (void)launch_k(gn_apply_kernel<1, false>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
-  else (void)launch_k(gn_apply_kernel<2, false>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+    if (U == 4) (void)launch_k(gn_apply_kernel<0, true, 4>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+    else (void)launch_k(gn_apply_kernel<0, true, 2>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  } else if (p.resample == 0) {
+    if (U == 4) (void)launch_k(gn_apply_kernel<0, false, 4>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+    else (void)launch_k(gn_apply_kernel<0, false, 2>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  } else if (p.resample == 1) (void)launch_k(gn_apply_kernel<1, false, 2>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  else (void)launch_k(gn_apply_kernel<2, false, 1>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
   return static_cast<int>(cudaGetLastError());
 }
 
