@@ -446,143 +446,6 @@ int launch_conv_in(const ConvInParams& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// output conv C -> 3|6 fused with the per-step update (warp per pixel, lanes across channels)
-// ------------------------------------------------------------------------------------------------
-constexpr int kConvOutPixPerWarp = 4;
-
-template <int CPL, int COUT>
-__global__ void __launch_bounds__(256) conv_out_kernel(ConvOutParams p) {
-  pdl_entry();
-  extern __shared__ float sw[];  // [9][CPL][COUT][32]
-  const int C = p.C;
-  for (int i = threadIdx.x; i < 9 * C * COUT; i += blockDim.x) {
-    const int o = i % COUT;
-    const int c = (i / COUT) % C;
-    const int tap = i / (COUT * C);
-    const int ln = c / CPL, j = c % CPL;
-    sw[((tap * CPL + j) * COUT + o) * 32 + ln] = p.w[i];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int HW = p.H * p.W;
-  const long long npix = static_cast<long long>(p.B) * HW;
-  const long long base = (static_cast<long long>(blockIdx.x) * 8 + warp) * kConvOutPixPerWarp;
-  int step = 0;
-  float k[8];
-  CallParams cp;
-  cp.step_noise = nullptr; cp.seed = 0; cp.sample_offset = 0; cp.update_kind = 0;
-  if (p.mode == 1) {
-    step = *p.tables.step;
-    cp = *p.call;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) k[i] = p.tables.coef[step * 8 + i];
-  }
-  for (int pi = 0; pi < kConvOutPixPerWarp; ++pi) {
-    const long long gp = base + pi;
-    if (gp >= npix) break;
-    const int b = static_cast<int>(gp / HW);
-    const int pix = static_cast<int>(gp - static_cast<long long>(b) * HW);
-    const int h = pix / p.W, w = pix - h * p.W;
-    float acc[COUT];
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
-      const __nv_bfloat16* src =
-          p.act + (static_cast<size_t>(b) * HW + static_cast<size_t>(hh) * p.W + ww) * C + lane * CPL;
-      float v[CPL];
-      if constexpr (CPL == 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(src);
-        unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
-        unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
-      } else if constexpr (CPL == 4) {
-        const uint2 u = *reinterpret_cast<const uint2*>(src);
-        unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
-      } else {
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(src);
-        unpack_bf16x2(u, v[0], v[1]);
-      }
-#pragma unroll
-      for (int j = 0; j < CPL; ++j)
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[o] += v[j] * sw[((tap * CPL + j) * COUT + o) * 32 + lane];
-    }
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) {
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
-      acc[o] += p.bias[o];
-    }
-    if (p.mode == 0) {
-      float val = 0.f;
-#pragma unroll
-      for (int o = 0; o < COUT; ++o) val = (lane == o) ? acc[o] : val;
-      if (lane < COUT) p.out_nchw[(static_cast<size_t>(b) * COUT + lane) * HW + pix] = val;
-    } else if (lane < 3) {
-      float eps = 0.f, vv = 0.f;
-#pragma unroll
-      for (int o = 0; o < 3; ++o) eps = (lane == o) ? acc[o] : eps;
-      if constexpr (COUT >= 6) {
-#pragma unroll
-        for (int o = 0; o < 3; ++o) vv = (lane == o) ? acc[3 + o] : vv;
-      }
-      float* xp = p.x + gp * 3 + lane;
-      const float xv = *xp;
-      const float z = cp.step_noise
-                          ? cp.step_noise[((static_cast<size_t>(step) * p.B + b) * 3 + lane) * HW + pix]
-                          : dp_normal(cp.seed, cp.sample_offset + b, static_cast<unsigned>(step) + 1u,
-                                      static_cast<unsigned>(pix), lane);
-      float xn;
-      if (cp.update_kind == 0) {
-        xn = k[0] * xv + k[1] * eps + k[2] * z;
-      } else {
-        // guided_diffusion/gaussian_diffusion.py:277-284,305,317-322,438-446
-        float x0 = k[0] * xv - k[1] * eps;
-        x0 = fminf(1.f, fmaxf(-1.f, x0));
-        const float mean = k[2] * x0 + k[3] * xv;
-        const float frac = (vv + 1.f) * 0.5f;
-        const float logvar = frac * k[4] + (1.f - frac) * k[5];
-        xn = mean + k[6] * expf(0.5f * logvar) * z;
-      }
-      *xp = xn;
-    }
-  }
-}
-
-template <int CPL, int COUT>
-static int launch_conv_out_t(const ConvOutParams& p, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(9) * p.C * COUT * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel<CPL, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done = true;
-  }
-  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
-  const long long per_block = 8LL * kConvOutPixPerWarp;
-  (void)launch_k(conv_out_kernel<CPL, COUT>, dim3(static_cast<unsigned>((npix + per_block - 1) / per_block)), dim3(256), smem, s, 1, p);
-  return static_cast<int>(cudaGetLastError());
-}
-
-int launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
-  const int cpl = p.C / 32;
-  if (p.Cout == 3) {
-    if (cpl == 2) return launch_conv_out_t<2, 3>(p, s);
-    if (cpl == 4) return launch_conv_out_t<4, 3>(p, s);
-    if (cpl == 8) return launch_conv_out_t<8, 3>(p, s);
-  } else if (p.Cout == 6) {
-    if (cpl == 2) return launch_conv_out_t<2, 6>(p, s);
-    if (cpl == 4) return launch_conv_out_t<4, 6>(p, s);
-    if (cpl == 8) return launch_conv_out_t<8, 6>(p, s);
-  }
-  return static_cast<int>(cudaErrorInvalidValue);
-}
-
-// ------------------------------------------------------------------------------------------------
 // per-step update from the output conv's result (fp32 [B*HW, ld], first Cout columns valid)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {

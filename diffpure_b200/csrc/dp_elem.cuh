@@ -55,18 +55,6 @@ struct CallParams {
   int update_kind;  // 0: x <- k0 x + k1 eps + k2 z ; 1: learned-range DDPM step ; 2: kind 0 + k3 x_init
 };
 
-struct ConvOutParams {
-  const __nv_bfloat16* act; const float* w; const float* bias;
-  int B, H, W, C, Cout;
-  // mode 0: write eps/out to `out_nchw` [B,Cout,H,W];  mode 1: fused per-step update of `x` (NHWC [B,H,W,3])
-  int mode;
-  float* out_nchw;
-  float* x;
-  StepTables tables;  // coef pitch is always 8
-  const CallParams* call;  // device
-};
-int launch_conv_out(const ConvOutParams& p, cudaStream_t s);
-
 // Per-step update from an fp32 eps buffer [B*H*W, ld] (written by the output conv run as a tensor-core GEMM):
 // mode 0 copies the first Cout columns to out_nchw, mode 1 applies the fused SDE / DDPM update to x (NHWC [.,3]).
 struct UpdateParams {

@@ -18,7 +18,7 @@ namespace {
 
 std::string g_create_error;
 
-enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_CONV_OUT, OP_ATTN_SMALL, OP_SOFTMAX,
+enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX,
               OP_GN_FINALIZE, OP_UPDATE };
 
 struct StatsReduce {
@@ -45,7 +45,6 @@ struct Op {
   dp_stats_desc stats;
   StatsReduce sred;
   dp::ConvInParams cin;
-  dp::ConvOutParams cout_;
   dp::AttnSmallParams attn;
   dp_softmax_desc smax;
   dp::UpdateParams upd;
@@ -155,15 +154,6 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       dp::ConvInParams p = op.cin;
       p.x = e->x_state;
       rc = dp::launch_conv_in(p, s);
-      break;
-    }
-    case OP_CONV_OUT: {
-      dp::ConvOutParams p = op.cout_;
-      p.mode = mode;
-      p.out_nchw = e->eps_out;
-      p.x = e->x_state;
-      p.call = e->d_call;
-      rc = dp::launch_conv_out(p, s);
       break;
     }
     case OP_ATTN_SMALL:
@@ -554,24 +544,6 @@ int dp_op_conv_in(dp_engine* e, const dp_conv_in_desc* d) {
   return DP_OK;
 }
 
-int dp_op_conv_out(dp_engine* e, const dp_conv_out_desc* d) {
-  if (!e || !d) return DP_ERR_INVALID;
-  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
-  if (int rc = ensure_run_state(e)) return rc;
-  if ((d->Cout != 3 && d->Cout != 6) || (d->C != 64 && d->C != 128 && d->C != 256))
-    return fail(e, DP_ERR_INVALID, "conv_out: Cout in {3,6}, C in {64,128,256}");
-  Op op;
-  op.kind = OP_CONV_OUT;
-  std::memset(&op.cout_, 0, sizeof(op.cout_));
-  op.cout_.act = static_cast<const __nv_bfloat16*>(d->act_bf16);
-  op.cout_.w = d->w; op.cout_.bias = d->bias;
-  op.cout_.B = d->B; op.cout_.H = d->H; op.cout_.W = d->W; op.cout_.C = d->C; op.cout_.Cout = d->Cout;
-  op.cout_.tables = tables_of(e, 8);
-  e->Cout = d->Cout;
-  e->ops.push_back(op);
-  return DP_OK;
-}
-
 int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d) {
   if (!e || !d) return DP_ERR_INVALID;
   if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
@@ -683,7 +655,6 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   DP_CUDA(e, cudaMemcpyAsync(e->d_call, &cp, sizeof(cp), cudaMemcpyHostToDevice, s));
   DP_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int), s));
   DP_CUDA(e, cudaStreamSynchronize(s));  // host staging buffers (coef8, cp) may go out of scope
-  // the conv_out node was captured with update_kind / ncoef of the program; patch through the tables
   const int HW = e->H * e->W;
   int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
                                  p->seed, p->sample_offset, s);

@@ -1,14 +1,17 @@
 // dp_gemm.cu -- persistent, warp-specialised tcgen05 implicit-GEMM convolution / GEMM kernel (sm_100a).
 //
-// Warp roles (256 threads, 1 CTA per SM):
+// Warp roles (128 control threads + 4 or 8 epilogue warps, 1 CTA per SM, persistent over tiles):
 //   warp 0 (one elected lane) : TMA producer   -- A halo tiles (4-D map, OOB zero fill = conv padding)
 //                                                 and weight tiles into a num_stages smem ring
 //   warp 1 (one elected lane) : tcgen05.mma issuer, 128 x BN x 16 per instruction, fp32 accum in TMEM,
 //                                                 two accumulator stages so the epilogue overlaps the next tile
 //   warp 2                    : TMEM allocator / deallocator
-//   warps 4..11               : epilogue (two warps per TMEM lane quadrant, alternating 32-column blocks): tcgen05.ld -> smem transpose -> fused bias / time-embedding add /
-//                               residual / scale / SiLU -> coalesced fp32|bf16 stores, plus deterministic
-//                               per-channel GroupNorm partial statistics of the tile; or row softmax.
+//   warps 4..                 : epilogue (BN = 128: two warps per TMEM lane quadrant, alternating 32-column blocks):
+//                               tcgen05.ld -> smem transpose -> fused bias / time-embedding add / residual / scale /
+//                               SiLU -> coalesced fp32|bf16 stores, plus deterministic per-channel GroupNorm partial
+//                               statistics of the tile; or the row-softmax numerator straight from TMEM.
+// CG = 2 runs the same roles on a CTA pair (cluster of 2, tcgen05 cta_group::2): a 256 x BN tile, each CTA staging its own
+// 128 rows of A and half of B, the leader CTA's warp 1 issuing the MMAs for both SMs (see Smem<> and the CG == 2 branches).
 #include "dp_gemm.cuh"
 #include "dp_launch.cuh"
 #include "dp_ptx.cuh"

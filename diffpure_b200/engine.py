@@ -159,10 +159,6 @@ class Engine:
                 d = _lib.ConvInDesc(self._p(a["w"]), self._p(a["bias"]), self._p(a["out"]), self._p(a["stats"]),
                                     a["B"], a["H"], a["W"], a["Cout"])
                 self._check(L.dp_op_conv_in(self.h, C.byref(d)), "dp_op_conv_in")
-            elif op.kind == "conv_out":
-                d = _lib.ConvOutDesc(self._p(a["act"]), self._p(a["w"]), self._p(a["bias"]), a["B"], a["H"], a["W"],
-                                     a["C"], a["Cout"])
-                self._check(L.dp_op_conv_out(self.h, C.byref(d)), "dp_op_conv_out")
             elif op.kind == "attn_small":
                 d = _lib.AttnSmallDesc(self._p(a["qkv"]), self._p(a["out"]), a["B"], a["T"], a["heads"], a["d"],
                                        a["scale"])
@@ -231,7 +227,7 @@ class Engine:
         self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), None), "dp_purify")
         return out
 
-    OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "conv_out", "attn_small",
+    OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "attn_small",
                 "softmax_rows", "gn_finalize", "update")
 
     def profile_ops(self, mode=0):

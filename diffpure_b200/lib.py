@@ -52,11 +52,6 @@ class ConvInDesc(C.Structure):
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int)]
 
 
-class ConvOutDesc(C.Structure):
-    _fields_ = [("act_bf16", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("B", C.c_int), ("H", C.c_int),
-                ("W", C.c_int), ("C", C.c_int), ("Cout", C.c_int)]
-
-
 class AttnSmallDesc(C.Structure):
     _fields_ = [("qkv_bf16", C.c_void_p), ("out_bf16", C.c_void_p), ("B", C.c_int), ("T", C.c_int),
                 ("heads", C.c_int), ("d", C.c_int), ("scale", C.c_float)]
@@ -94,7 +89,6 @@ SYMBOLS = {
     "dp_op_gn_apply": (C.c_int, [C.c_void_p, C.POINTER(GnDesc)]),
     "dp_op_stats": (C.c_int, [C.c_void_p, C.POINTER(StatsDesc)]),
     "dp_op_conv_in": (C.c_int, [C.c_void_p, C.POINTER(ConvInDesc)]),
-    "dp_op_conv_out": (C.c_int, [C.c_void_p, C.POINTER(ConvOutDesc)]),
     "dp_op_attn_small": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallDesc)]),
     "dp_op_softmax_rows": (C.c_int, [C.c_void_p, C.POINTER(SoftmaxDesc)]),
     "dp_op_update": (C.c_int, [C.c_void_p, C.POINTER(UpdateDesc)]),

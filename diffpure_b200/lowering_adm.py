@@ -13,7 +13,7 @@ from types import SimpleNamespace
 import torch
 
 from .lowering_common import Act, act_seg, lower_attention, new_act, pack_conv1x1, pack_conv3x3, pack_conv_in, \
-    pack_conv_out, pad_rows
+    pad_rows
 from .program import Program, view
 
 EPS = 1e-5

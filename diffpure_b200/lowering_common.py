@@ -37,11 +37,6 @@ def pack_conv_in(w):
     return w.permute(2, 3, 1, 0).reshape(27, w.shape[0]).contiguous()
 
 
-def pack_conv_out(w):
-    """[Cout, C, 3, 3] -> [9, C, Cout]."""
-    return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
-
-
 def pad_rows(w, mult=128):
     """Zero-pad the leading (output) dimension to a multiple of `mult`."""
     n = w.shape[0]

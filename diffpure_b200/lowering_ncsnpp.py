@@ -17,8 +17,7 @@ from types import SimpleNamespace
 
 import torch
 
-from .lowering_common import INV_SQRT2, Act, act_seg, new_act, pack_conv1x1, pack_conv3x3, pack_conv_in, \
-    pack_conv_out, pad_rows
+from .lowering_common import INV_SQRT2, Act, act_seg, new_act, pack_conv1x1, pack_conv3x3, pack_conv_in, pad_rows
 from .program import Program, view
 
 

@@ -113,9 +113,6 @@ class Program:
     def conv_in(self, w, bias, out, stats, B, H, W, Cout):
         self.add("conv_in", w=view(w), bias=view(bias), out=view(out), stats=view(stats), B=B, H=H, W=W, Cout=Cout)
 
-    def conv_out(self, act, w, bias, B, H, W, C, Cout):
-        self.add("conv_out", act=view(act), w=view(w), bias=view(bias), B=B, H=H, W=W, C=C, Cout=Cout)
-
     def update(self, eps, ld, B, H, W, Cout):
         self.add("update", eps=view(eps), ld=ld, B=B, H=H, W=W, Cout=Cout)
 

@@ -18,9 +18,10 @@
  *                       (layerspp.py:219,231,245-258; unet.py:244-260; nn.py:25-27; unet_ddpm.py:40-41,55-60)
  *   dp_op_stats      <- GroupNorm statistics of a tensor not produced by dp_op_gemm
  *   dp_op_conv_in    <- the 3->C input conv        (ncsnpp.py:268, unet.py:486, unet_ddpm.py:229)
- *   dp_op_conv_out   <- the C->3|6 output conv fused with the per-step update
+ *   dp_op_update     <- the per-step update behind the C->3|6 output conv (itself a dp_op_gemm padded to 8 columns)
  *                       (ncsnpp.py:371-374 + runners/diffpure_sde.py:86-147 + torchsde Euler step;
- *                        guided_diffusion/gaussian_diffusion.py:240-334,403-447; runners/diffpure_ddpm.py:37-54)
+ *                        guided_diffusion/gaussian_diffusion.py:240-334,403-447; runners/diffpure_ddpm.py:37-54;
+ *                        runners/diffpure_ode.py:90-131; runners/diffpure_ldsde.py:92-148)
  *   dp_op_attn_small <- whole-sequence attention for short sequences (T <= 64)
  * Threading: one engine per (process, device); calls on an engine are stream-ordered and not re-entrant.
  * Ownership: the caller owns every pointer it passes to dp_unet_forward / dp_purify; the engine owns
@@ -136,15 +137,8 @@ typedef struct {
   int B, H, W, Cout;
 } dp_conv_in_desc;
 
-typedef struct {
-  const void* act_bf16; /* [B,H,W,C] */
-  const float* w;       /* [9][C][Cout] fp32 */
-  const float* bias;    /* [Cout] */
-  int B, H, W, C, Cout; /* Cout = 3 or 6 */
-} dp_conv_out_desc;
-
 /* Output stage when the C->3|6 conv runs as a dp_op_gemm (N padded to 8): consumes its fp32 result and either
- * returns it (dp_unet_forward) or applies the fused per-step update of dp_purify. Alternative to dp_op_conv_out. */
+ * returns it (dp_unet_forward) or applies the fused per-step update of dp_purify. */
 typedef struct {
   const float* eps; int ld; /* fp32 [B*H*W, ld], first Cout columns valid */
   int B, H, W, Cout;
@@ -162,7 +156,6 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d);
 int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d);
 int dp_op_stats(dp_engine* e, const dp_stats_desc* d);
 int dp_op_conv_in(dp_engine* e, const dp_conv_in_desc* d);
-int dp_op_conv_out(dp_engine* e, const dp_conv_out_desc* d);
 int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d);
 int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d);
 int dp_op_update(dp_engine* e, const dp_update_desc* d);
@@ -202,7 +195,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
- * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 conv_out,7 attn_small,8 softmax_rows, 9 gn_finalize, 10 update,
+ * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 attn_small,7 softmax_rows,8 gn_finalize,9 update,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

@@ -18,7 +18,7 @@ from program_interp import Interp  # noqa: E402
 
 def written_tensors(op):
     keys = {"embed": ["out"], "gemm": ["out_f32", "out_bf16", "stats", "rowsum_out"],
-            "gn_apply": ["out_bf16", "raw_bf16", "raw_f32"], "conv_in": ["out", "stats"], "conv_out": [],
+            "gn_apply": ["out_bf16", "raw_bf16", "raw_f32"], "conv_in": ["out", "stats"],
             "attn_small": ["out"]}[op.kind]
     return [op.args[k] for k in keys if op.args.get(k) is not None]
 

@@ -216,11 +216,6 @@ class Interp:
             sb, so = self.flat(stats)
             sb[so:so + st.numel()] = st.reshape(-1)
 
-    def op_conv_out(self, act, w, bias, B, H, W, C, Cout):
-        a = self.rd(act, (B, H, W, C)).permute(0, 3, 1, 2)
-        wt = self.rd(w, (3, 3, C, Cout)).permute(3, 2, 0, 1).contiguous()
-        self.out = F.conv2d(a, wt, self.rd(bias, (Cout,)), padding=1)
-
     def op_update(self, eps, ld, B, H, W, Cout):
         e = self.rd(eps, (B, H, W, Cout), (H * W * ld, W * ld, ld, 1))
         self.out = e.permute(0, 3, 1, 2).contiguous()
