@@ -1,0 +1,134 @@
+"""Shared pieces of the five runners.
+
+* `VPScore`: the continuous VP-SDE quantities (beta(t), the eps -> score conversion for both score-network conventions)
+  behind the three "SDE object" classes the reference exposes to torchsde / torchdiffeq (`RevVPSDE`, `VPODE`, `LDSDE`).
+* `PurifyRunner`: the control flow every `image_editing_sample` shares around `Engine.purify` -- device choice, the
+  `bs_id < 2` image dumps under `log_dir/bs{bs_id}_{tag}`, the `sample_step` passes -- so each runner only states its
+  schedule and update kind.
+"""
+import os
+import random
+
+import numpy as np
+import torch
+
+
+def _extract_into_tensor(arr_or_func, timesteps, broadcast_shape):
+    """Table lookup or callable evaluated at `timesteps`, broadcast to `broadcast_shape` (runners/diffpure_sde.py:23-39)."""
+    if callable(arr_or_func):
+        res = arr_or_func(timesteps).float()
+    else:
+        res = arr_or_func.to(device=timesteps.device)[timesteps].float()
+    while len(res.shape) < len(broadcast_shape):
+        res = res[..., None]
+    return res.expand(broadcast_shape)
+
+
+class VPScore(torch.nn.Module):
+    """beta_t = beta_0 + t (beta_1 - beta_0) and score(x, t) from the eps network, on flattened states (B, C*H*W)."""
+
+    def __init__(self, model, score_type, beta_min, beta_max, N, img_shape, model_kwargs):
+        super().__init__()
+        self.model = model
+        self.score_type = score_type
+        self.model_kwargs = model_kwargs
+        self.img_shape = img_shape
+        self.beta_0, self.beta_1, self.N = beta_min, beta_max, N
+        self.discrete_betas = torch.linspace(beta_min / N, beta_max / N, N)
+        self.alphas = 1. - self.discrete_betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.sqrt_alphas_cumprod = torch.sqrt(self.alphas_cumprod)
+        self.sqrt_1m_alphas_cumprod = torch.sqrt(1. - self.alphas_cumprod)
+        self.alphas_cumprod_cont = lambda t: torch.exp(-0.5 * (beta_max - beta_min) * t ** 2 - beta_min * t)
+        self.sqrt_1m_alphas_cumprod_neg_recip_cont = lambda t: -1. / torch.sqrt(1. - self.alphas_cumprod_cont(t))
+
+    def _scale_timesteps(self, t):
+        assert torch.all(t <= 1) and torch.all(t >= 0), f't has to be in [0, 1], but get {t} with shape {t.shape}'
+        return (t.float() * self.N).long()
+
+    def beta(self, t):
+        return self.beta_0 + t * (self.beta_1 - self.beta_0)
+
+    def score(self, t, x):
+        """t: (B,) forward time, x: (B, D) -> (B, D)."""
+        assert x.ndim == 2 and np.prod(self.img_shape) == x.shape[1], x.shape
+        x_img = x.view(-1, *self.img_shape)
+        if self.score_type == 'guided_diffusion':      # discrete-time eps(+var) network, eps -> score with sigma(t)
+            eps = self.model(x_img, self._scale_timesteps(t))
+            eps, _ = torch.split(eps, self.img_shape[0], dim=1)
+            scale = _extract_into_tensor(self.sqrt_1m_alphas_cumprod_neg_recip_cont, t, x.shape)
+            return scale * eps.reshape(x.shape[0], -1)
+        if self.score_type == 'score_sde':             # continuous-time network fed t*999 (score_sde/models/utils.py:149)
+            eps = self.model(x_img, t * 999)
+            log_mean_coeff = -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+            std = torch.sqrt(1. - torch.exp(2. * log_mean_coeff))                      # sde_lib.py:149-153
+            return (-eps / std[:, None, None, None]).reshape(x.shape[0], -1)
+        raise NotImplementedError(f'Unknown score type in RevVPSDE: {self.score_type}!')
+
+
+class _Dump:
+    """The reference's per-batch image dumps (only for the first two batches)."""
+
+    def __init__(self, args, bs_id, tag):
+        if tag is None:
+            tag = 'rnd' + str(random.randint(0, 10000))
+        self.dir = os.path.join(args.log_dir, 'bs' + str(bs_id) + '_' + tag)
+        self.on = bs_id < 2 and getattr(args, "save_images", True)
+        if self.on:
+            os.makedirs(self.dir, exist_ok=True)
+
+    def image(self, name, x):
+        if self.on:
+            import torchvision.utils as tvu
+            tvu.save_image((x + 1) * 0.5, os.path.join(self.dir, name))
+
+    def tensor(self, name, x):
+        if self.on:
+            torch.save(x, os.path.join(self.dir, name))
+
+
+class PurifyRunner(torch.nn.Module):
+    """Base of the runner classes: `self.model` is a `ScoreModel` (engine factory)."""
+
+    differentiable_error = None     # message raised for inputs that require grad (None: the runner is no_grad anyway)
+    device_from_input = False       # Diffusion takes the device from the input image (runners/diffpure_ddpm.py:126,129)
+
+    def _setup(self, args, config, device):
+        self.args = args
+        self.config = config
+        if device is None:
+            device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
+        self.sample_offset = 0      # global index of this shard's first sample (multi-GPU sharding)
+        self.last_seed = None
+
+    def _call_seed(self, seed, it):
+        """Seed of one pass: drawn from NumPy's global RNG (as torchsde's BrownianInterval does without entropy) or
+        derived from the caller's."""
+        s = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed) + it
+        self.last_seed = s
+        return s
+
+    def _open(self, img, bs_id, tag):
+        assert isinstance(img, torch.Tensor)
+        if self.differentiable_error and torch.is_grad_enabled() and img.requires_grad:
+            raise NotImplementedError(self.differentiable_error)
+        assert img.ndim == 4, img.ndim
+        if self.device_from_input:
+            dev = img.device if img.device.type == "cuda" else self.device
+        else:
+            dev = self.device if self.device.type == "cuda" else img.device
+        x0 = img.to(dev)
+        dump = _Dump(self.args, bs_id, tag)
+        dump.image('original_input.png', x0)
+        return x0, dev, dump
+
+    def _passes(self, x0, dump, one_pass):
+        """`sample_step` purification passes, each starting from the previous one's output; returns their concatenation."""
+        xs = []
+        for it in range(self.args.sample_step):
+            x0 = one_pass(it, x0)
+            dump.tensor(f'samples_{it}.pth', x0)
+            dump.image(f'samples_{it}.png', x0)
+            xs.append(x0)
+        return torch.cat(xs, dim=0)
