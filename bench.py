@@ -359,7 +359,7 @@ def main():
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
 
     cpu = None
-    if not args.no_cpu_baseline and args.config == "cifar10":
+    if not args.no_cpu_baseline and args.config == "cifar10" and world == 1:   # the contract: rank 0 at N=1 only
         rate, dt, threads = cpu_reference_rate(16, 30)         # ~10-15 s of CPU work
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"oracle CPU port of the reference loop, batch 16 (configs[0]), 30 of 100 Euler steps "
