@@ -32,10 +32,9 @@ struct GnParams {
   int B, H, W, groups; float eps; int silu; int resample;
   __nv_bfloat16* out; __nv_bfloat16* raw; float* raw_f32;
 };
-// finalize: partial statistics -> ss [B][2][C] (scale, shift); apply: streaming normalise (+SiLU, resample) -> bf16.
-// `ss == nullptr` in apply = identity (cast / resample only).
-int launch_gn_finalize(const GnParams& p, float* ss, cudaStream_t s);
-int launch_gn_apply(const GnParams& p, const float* ss, int num_sms, cudaStream_t s);
+// Streaming normalise (+SiLU, FiLM, resample, concat) -> bf16; every CTA folds its sample's partial statistics into the
+// per-channel scale / shift itself. `stats0 == nullptr` = identity (cast / resample only).
+int launch_gn_apply(const GnParams& p, int num_sms, cudaStream_t s);
 
 // fp32 [B, HW, C] -> per-channel partial (sum, sumsq) [B][P][C][2], P = ceil(HW / 128)
 int launch_stats(const float* src, float* stats, int B, int HW, int C, cudaStream_t s);

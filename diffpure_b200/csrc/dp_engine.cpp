@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,8 +19,7 @@ namespace {
 
 std::string g_create_error;
 
-enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX,
-              OP_GN_FINALIZE, OP_UPDATE };
+enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX, OP_UPDATE };
 
 struct StatsReduce {
   const float* in;
@@ -58,6 +58,7 @@ struct dp_engine {
   mutable std::string err;
   std::vector<void*> buffers;
   std::vector<size_t> sizes;
+  std::vector<char> owned;  // 0: borrowed from the caller (dp_buffer_adopt), never freed here
   size_t total_bytes = 0;
   std::vector<Op> ops;
   bool finalized = false;
@@ -72,9 +73,10 @@ struct dp_engine {
   float* d_coef = nullptr;
   int table_cap = 0;
   dp::CallParams* d_call = nullptr;
-  float* gn_ss = nullptr;  // [B][2][C] scale/shift scratch shared by all GroupNorm ops (stream-ordered)
-  size_t gn_ss_floats = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // private stream: capture, profiling, calls made with stream == NULL
+  cudaStream_t last_stream = nullptr;  // stream of the latest dp_unet_forward / dp_purify (dp_buffer_read waits for it)
+  float* h_stage = nullptr;            // pinned staging of the per-call tables: coef [cap][8], cond [cap], CallParams
+  cudaEvent_t staging_done = nullptr;
   cudaGraphExec_t g_forward = nullptr, g_step = nullptr;
 };
 
@@ -121,6 +123,8 @@ int ensure_run_state(dp_engine* e) {
   DP_CUDA(e, cudaMemset(e->d_coef, 0, sizeof(float) * e->table_cap * 8));
   DP_CUDA(e, cudaMalloc(&e->d_call, sizeof(dp::CallParams)));
   DP_CUDA(e, cudaMemset(e->d_call, 0, sizeof(dp::CallParams)));
+  DP_CUDA(e, cudaMallocHost(&e->h_stage, sizeof(float) * e->table_cap * 9 + sizeof(dp::CallParams) + 64));
+  DP_CUDA(e, cudaEventCreateWithFlags(&e->staging_done, cudaEventDisableTiming));
   return DP_OK;
 }
 
@@ -139,10 +143,7 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s, op.cg);
       break;
     case OP_GN:
-      rc = dp::launch_gn_apply(op.gn, op.gn.stats0 ? e->gn_ss : nullptr, e->num_sms, s);
-      break;
-    case OP_GN_FINALIZE:
-      rc = dp::launch_gn_finalize(op.gn, e->gn_ss, s);
+      rc = dp::launch_gn_apply(op.gn, e->num_sms, s);
       break;
     case OP_STATS:
       rc = dp::launch_stats(op.stats.src, op.stats.stats, op.stats.B, op.stats.HW, op.stats.C, s);
@@ -266,7 +267,8 @@ void dp_destroy(dp_engine* e) {
   cudaDeviceSynchronize();
   if (e->g_forward) cudaGraphExecDestroy(e->g_forward);
   if (e->g_step) cudaGraphExecDestroy(e->g_step);
-  for (void* p : e->buffers) cudaFree(p);
+  for (size_t i = 0; i < e->buffers.size(); ++i)
+    if (e->owned[i]) cudaFree(e->buffers[i]);
   cudaFree(e->x_state);
   cudaFree(e->x_init);
   cudaFree(e->eps_out);
@@ -275,7 +277,8 @@ void dp_destroy(dp_engine* e) {
   cudaFree(e->d_cond);
   cudaFree(e->d_coef);
   cudaFree(e->d_call);
-  cudaFree(e->gn_ss);
+  cudaFreeHost(e->h_stage);
+  if (e->staging_done) cudaEventDestroy(e->staging_done);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -302,7 +305,22 @@ int dp_buffer_alloc(dp_engine* e, size_t bytes, int* buf_id) {
   DP_CUDA(e, cudaMemset(p, 0, padded ? padded : 256));
   e->buffers.push_back(p);
   e->sizes.push_back(bytes);
+  e->owned.push_back(1);
   e->total_bytes += padded;
+  *buf_id = static_cast<int>(e->buffers.size()) - 1;
+  return DP_OK;
+}
+
+int dp_buffer_adopt(dp_engine* e, void* device_ptr, size_t bytes, int* buf_id) {
+  if (!e || !buf_id || !device_ptr) return DP_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(device_ptr) & 255u) return fail(e, DP_ERR_INVALID, "dp_buffer_adopt: pointer must be 256-byte aligned");
+  cudaPointerAttributes at;
+  DP_CUDA(e, cudaPointerGetAttributes(&at, device_ptr));
+  if (at.type != cudaMemoryTypeDevice || at.device != e->device)
+    return fail(e, DP_ERR_INVALID, "dp_buffer_adopt: not device memory of this engine's device");
+  e->buffers.push_back(device_ptr);
+  e->sizes.push_back(bytes);
+  e->owned.push_back(0);
   *buf_id = static_cast<int>(e->buffers.size()) - 1;
   return DP_OK;
 }
@@ -323,6 +341,7 @@ int dp_buffer_read(dp_engine* e, int buf_id, size_t offset, void* host_dst, size
   if (!e || buf_id < 0 || buf_id >= static_cast<int>(e->buffers.size())) return DP_ERR_INVALID;
   if (offset + bytes > e->sizes[buf_id]) return fail(e, DP_ERR_INVALID, "dp_buffer_read out of range");
   DP_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->last_stream && e->last_stream != e->stream) DP_CUDA(e, cudaStreamSynchronize(e->last_stream));
   DP_CUDA(e, cudaMemcpy(host_dst, static_cast<char*>(e->buffers[buf_id]) + offset, bytes, cudaMemcpyDeviceToHost));
   return DP_OK;
 }
@@ -493,22 +512,6 @@ int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d) {
     e->ops.push_back(r);
     if (which) { p.stats1 = r.sred.out; p.P1 = 1; } else { p.stats0 = r.sred.out; p.P0 = 1; }
   }
-  if (p.stats0) {
-    const size_t need = static_cast<size_t>(d->B) * 2 * C;
-    if (need > e->gn_ss_floats) {
-      if (!e->ops.empty() && e->gn_ss) {
-        // earlier ops captured the old pointer by value only at launch time (read from the engine), so growing is safe
-      }
-      cudaFree(e->gn_ss);
-      e->gn_ss = nullptr;
-      DP_CUDA(e, cudaMalloc(&e->gn_ss, need * sizeof(float)));
-      e->gn_ss_floats = need;
-    }
-    Op f;
-    f.kind = OP_GN_FINALIZE;
-    f.gn = p;
-    e->ops.push_back(f);
-  }
   Op op;
   op.kind = OP_GN;
   op.gn = p;
@@ -610,20 +613,35 @@ int dp_finalize(dp_engine* e, int B, int H, int W) {
   return DP_OK;
 }
 
+// Stream contract of dp_unet_forward / dp_purify: `stream` != NULL -> all work is enqueued on that stream (ordered behind
+// whatever the caller enqueued before, e.g. the producer of x) and the call returns without synchronising; the caller
+// synchronises that stream before reading the output on the host. `stream` == NULL -> the engine's private stream is
+// used and the call blocks: it first waits for the caller's default-stream work, then for its own result. The engine's buffers are shared run state: calls on one engine
+// must not overlap (not re-entrant), whichever streams they use.
+static int pick_stream(dp_engine* e, void* stream, cudaStream_t* out) {
+  if (stream) {
+    *out = static_cast<cudaStream_t>(stream);
+    return DP_OK;
+  }
+  DP_CUDA(e, cudaStreamSynchronize(nullptr));  // the caller's default-stream work (e.g. the producer of x) is complete
+  *out = e->stream;
+  return DP_OK;
+}
+
 int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float* out_nchw, void* stream) {
   if (!e || !x_nchw || !cond || !out_nchw) return DP_ERR_INVALID;
   if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
-  cudaStream_t user = static_cast<cudaStream_t>(stream);
   DP_CUDA(e, cudaSetDevice(e->device));
-  DP_CUDA(e, cudaStreamSynchronize(user));  // inputs produced on the caller's stream are complete
+  cudaStream_t s = nullptr;
+  if (int rc0 = pick_stream(e, stream, &s)) return rc0;
+  e->last_stream = s;
   const int HW = e->H * e->W;
-  int rc = dp::launch_init_state(x_nchw, x_nchw, e->x_state, e->B, 3, HW, 1.0f, 0.0f, 0, 0, e->stream);
+  int rc = dp::launch_init_state(x_nchw, x_nchw, e->x_state, e->B, 3, HW, 1.0f, 0.0f, 0, 0, s);
   if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
-  DP_CUDA(e, cudaMemcpyAsync(e->cond_per_sample, cond, sizeof(float) * e->B, cudaMemcpyDeviceToDevice, e->stream));
-  DP_CUDA(e, cudaGraphLaunch(e->g_forward, e->stream));
-  DP_CUDA(e, cudaMemcpyAsync(out_nchw, e->eps_out, sizeof(float) * e->B * e->Cout * HW, cudaMemcpyDeviceToDevice,
-                             e->stream));
-  DP_CUDA(e, cudaStreamSynchronize(e->stream));
+  DP_CUDA(e, cudaMemcpyAsync(e->cond_per_sample, cond, sizeof(float) * e->B, cudaMemcpyDeviceToDevice, s));
+  DP_CUDA(e, cudaGraphLaunch(e->g_forward, s));
+  DP_CUDA(e, cudaMemcpyAsync(out_nchw, e->eps_out, sizeof(float) * e->B * e->Cout * HW, cudaMemcpyDeviceToDevice, s));
+  if (!stream) DP_CUDA(e, cudaStreamSynchronize(s));
   return DP_OK;
 }
 
@@ -636,25 +654,30 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   const int want = p->update_kind == DP_UPDATE_LEARNED_RANGE ? 6 : 3;
   if (e->Cout != want && !(p->update_kind != DP_UPDATE_LEARNED_RANGE && e->Cout == 6))
     return fail(e, DP_ERR_INVALID, "update_kind does not match the model's output channels");
-  cudaStream_t user = static_cast<cudaStream_t>(stream);
   DP_CUDA(e, cudaSetDevice(e->device));
-  DP_CUDA(e, cudaStreamSynchronize(user));
-  cudaStream_t s = e->stream;
-  // per-step tables: the captured graph reads cond[*step] / coef[*step][:]
-  std::vector<float> coef8(static_cast<size_t>(p->steps) * 8, 0.f);
+  cudaStream_t s = nullptr;
+  if (int rc0 = pick_stream(e, stream, &s)) return rc0;
+  e->last_stream = s;
+  // per-step tables: the captured graph reads cond[*step] / coef[*step][:], laid out with a fixed pitch of 8 so the
+  // graph's kernel parameters never change. Staged through engine-owned pinned memory: the previous call's copies have
+  // completed before it is rewritten (cudaEventSynchronize on the staging event).
+  DP_CUDA(e, cudaEventSynchronize(e->staging_done));
+  float* coef8 = e->h_stage;
+  float* hcond = e->h_stage + static_cast<size_t>(e->table_cap) * 8;
+  dp::CallParams* cp = reinterpret_cast<dp::CallParams*>(hcond + e->table_cap);
+  std::memset(coef8, 0, sizeof(float) * static_cast<size_t>(p->steps) * 8);
   for (int i = 0; i < p->steps; ++i)
     for (int j = 0; j < p->ncoef; ++j) coef8[static_cast<size_t>(i) * 8 + j] = p->coef[static_cast<size_t>(i) * p->ncoef + j];
-  // tables are laid out with a fixed pitch of 8 so the graph's kernel parameters never change
-  DP_CUDA(e, cudaMemcpyAsync(e->d_cond, p->cond, sizeof(float) * p->steps, cudaMemcpyHostToDevice, s));
-  DP_CUDA(e, cudaMemcpyAsync(e->d_coef, coef8.data(), sizeof(float) * coef8.size(), cudaMemcpyHostToDevice, s));
-  dp::CallParams cp;
-  cp.step_noise = p->step_noise;
-  cp.seed = p->seed;
-  cp.sample_offset = p->sample_offset;
-  cp.update_kind = p->update_kind;
-  DP_CUDA(e, cudaMemcpyAsync(e->d_call, &cp, sizeof(cp), cudaMemcpyHostToDevice, s));
+  std::memcpy(hcond, p->cond, sizeof(float) * p->steps);
+  cp->step_noise = p->step_noise;
+  cp->seed = p->seed;
+  cp->sample_offset = p->sample_offset;
+  cp->update_kind = p->update_kind;
+  DP_CUDA(e, cudaMemcpyAsync(e->d_cond, hcond, sizeof(float) * p->steps, cudaMemcpyHostToDevice, s));
+  DP_CUDA(e, cudaMemcpyAsync(e->d_coef, coef8, sizeof(float) * static_cast<size_t>(p->steps) * 8, cudaMemcpyHostToDevice, s));
+  DP_CUDA(e, cudaMemcpyAsync(e->d_call, cp, sizeof(*cp), cudaMemcpyHostToDevice, s));
+  DP_CUDA(e, cudaEventRecord(e->staging_done, s));
   DP_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int), s));
-  DP_CUDA(e, cudaStreamSynchronize(s));  // host staging buffers (coef8, cp) may go out of scope
   const int HW = e->H * e->W;
   int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
                                  p->seed, p->sample_offset, s);
@@ -670,7 +693,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   for (int i = 0; i < p->steps; ++i) DP_CUDA(e, cudaGraphLaunch(e->g_step, s));
   rc = dp::launch_nhwc_to_nchw(e->x_state, out_nchw, e->B, 3, HW, s);
   if (rc) return fail(e, DP_ERR_CUDA, "nhwc_to_nchw launch failed");
-  DP_CUDA(e, cudaStreamSynchronize(s));
+  if (!stream) DP_CUDA(e, cudaStreamSynchronize(s));
   return DP_OK;
 }
 

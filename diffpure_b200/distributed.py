@@ -31,8 +31,29 @@ def broadcast_state_dict(sd, src=0, device="cpu"):
     return out
 
 
-def gather_shards(local, world):
-    """all_gather of equally-sized shards, concatenated in rank order (= global sample order)."""
+def broadcast_blob(blob, src=0):
+    """The data-parallel weight distribution: rank `src` packs and uploads the constants once, every other rank builds
+    only the layout (`WeightBlob(program, device, upload=False)`) and receives the packed bytes with ONE broadcast."""
+    blob.broadcast(src)
+    return blob
+
+
+def gather_shards(local, world, total=None):
+    """all_gather of the per-rank shards, concatenated in rank order (= global sample order). Shards produced by
+    `shard_range` differ by at most one sample: every rank pads to the largest shard and the padding is trimmed after the
+    collective (`total` = global sample count; None = equal shards)."""
+    local = local.contiguous()
+    if total is None:
+        bufs = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(bufs, local)
+        return torch.cat(bufs, dim=0)
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    sizes = [b - a for a, b in sizes]
+    assert local.shape[0] == sizes[dist.get_rank()], (local.shape[0], sizes)
+    big = max(sizes)
+    if local.shape[0] < big:
+        pad = torch.zeros((big - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], dim=0)
     bufs = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(bufs, local.contiguous())
-    return torch.cat(bufs, dim=0)
+    dist.all_gather(bufs, local)
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)

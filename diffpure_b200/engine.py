@@ -23,8 +23,56 @@ def _to_bytes(t, dtype):
     return t.to(torch.float32).numpy().tobytes()
 
 
+class WeightBlob:
+    """All constants of a lowered model (bf16 weights, fp32 biases / norm parameters / tables) packed into ONE device
+    allocation: one upload, one NCCL broadcast, shared by the engines of every batch size on that device.
+
+    The memory is a torch uint8 CUDA tensor (PyTorch = device memory + collectives only); engines adopt its pointer
+    through dp_buffer_adopt. `layout` maps constant name -> (byte offset, byte size)."""
+
+    def __init__(self, program: Program, device, upload=True):
+        consts = [t for t in program.tensors if t.init is not None]
+        self.layout, total = {}, 0
+        for t in consts:
+            self.layout[t.name] = (total, t.nbytes)
+            total += _align(t.nbytes)
+        self.nbytes = total
+        # ("cpu" is accepted for the host-logic tests of packing / broadcast; engines only adopt CUDA blobs)
+        self.device = torch.device(device) if isinstance(device, (str, torch.device)) else torch.device("cuda", int(device))
+        self.data = torch.empty(max(total, 256), dtype=torch.uint8, device=self.device)
+        assert self.data.data_ptr() % 256 == 0 or self.device.type == "cpu"
+        if upload:
+            host = torch.zeros(max(total, 256), dtype=torch.uint8)
+            if self.device.type == "cuda":
+                host = host.pin_memory()
+            for t in consts:
+                off, n = self.layout[t.name]
+                src = t.init.detach().cpu().contiguous()
+                src = src.to(torch.bfloat16) if t.dtype == "bf16" else src.to(torch.float32)
+                host[off:off + n] = src.view(torch.uint8).reshape(-1)
+            self.data.copy_(host, non_blocking=False)
+
+    def matches(self, program: Program):
+        consts = [t for t in program.tensors if t.init is not None]
+        return len(consts) == len(self.layout) and all(
+            t.name in self.layout and self.layout[t.name][1] == t.nbytes for t in consts)
+
+    def broadcast(self, src=0):
+        """One collective for all weights: the packed blob itself (NCCL; rank `src` holds the real values)."""
+        import torch.distributed as dist
+        dist.broadcast(self.data, src=src)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def tensor(self, name, dtype):
+        """Host copy of one constant (tests)."""
+        off, n = self.layout[name]
+        raw = self.data[off:off + n].cpu()
+        return raw.view(torch.bfloat16).float() if dtype == "bf16" else raw.view(torch.float32)
+
+
 class Engine:
-    def __init__(self, program: Program, device=0, pool=True):
+    def __init__(self, program: Program, device=0, pool=True, blob: WeightBlob = None):
         self.lib = _lib.load()
         self.program = program
         self.device = int(device)
@@ -40,10 +88,12 @@ class Engine:
         self.const_bytes = 0
         self.act_bytes = 0
         try:
-            self._upload_constants()
-            self._place_activations(pool)
-            self._emit_ops()
-            self._check(self.lib.dp_finalize(self.h, self.B, self.H, self.W), "dp_finalize")
+            with torch.cuda.device(self.device):
+                self.blob = blob if blob is not None else WeightBlob(program, self.device)
+                self._adopt_constants()
+                self._place_activations(pool)
+                self._emit_ops()
+                self._check(self.lib.dp_finalize(self.h, self.B, self.H, self.W), "dp_finalize")
         except Exception:
             self.close()
             raise
@@ -57,28 +107,25 @@ class Engine:
         self._check(self.lib.dp_buffer_alloc(self.h, nbytes, C.byref(bid)), "dp_buffer_alloc")
         return bid.value, self.lib.dp_buffer_ptr(self.h, bid.value)
 
-    def _upload_constants(self):
-        """All weights / tables go into one blob (one allocation, one upload; one NCCL broadcast when sharded)."""
-        consts = [t for t in self.program.tensors if t.init is not None]
-        offs, total = {}, 0
-        for t in consts:
-            offs[t.index] = total
-            total += _align(t.nbytes)
-        blob = bytearray(total)
-        for t in consts:
-            b = _to_bytes(t.init, t.dtype)
-            assert len(b) == t.nbytes, (t.name, len(b), t.nbytes)
-            blob[offs[t.index]:offs[t.index] + len(b)] = b
-        self.const_bytes = total
-        if total == 0:
+    def _adopt_constants(self):
+        """The program's constants live in the (possibly shared) weight blob; the engine only records their addresses."""
+        blob = self.blob
+        if blob.device.type != "cuda" or blob.device.index != self.device:
+            raise ValueError("weight blob lives on another device")
+        if not blob.matches(self.program):
+            raise ValueError("weight blob layout does not match this program's constants")
+        self.const_bytes = blob.nbytes
+        if blob.nbytes == 0:
             return
-        bid, base = self._alloc(total)
-        buf = (C.c_char * total).from_buffer(blob)
-        self._check(self.lib.dp_buffer_write(self.h, bid, 0, C.addressof(buf), total), "dp_buffer_write")
-        self.weights_buffer = (bid, base, total)
-        for t in consts:
-            self._ptr[t.index] = base + offs[t.index]
-            self._loc[t.index] = (bid, offs[t.index])
+        bid = C.c_int()
+        self._check(self.lib.dp_buffer_adopt(self.h, blob.data.data_ptr(), blob.nbytes, C.byref(bid)), "dp_buffer_adopt")
+        base = blob.data.data_ptr()
+        self.weights_buffer = (bid.value, base, blob.nbytes)
+        for t in self.program.tensors:
+            if t.init is not None:
+                off = blob.layout[t.name][0]
+                self._ptr[t.index] = base + off
+                self._loc[t.index] = (bid.value, off)
 
     def _place_activations(self, pool):
         prog = self.program
@@ -185,6 +232,10 @@ class Engine:
     def _dev(self):
         return torch.device("cuda", self.device)
 
+    def _stream(self):
+        st = torch.cuda.current_stream(self._dev()).cuda_stream
+        return C.c_void_p(st) if st else None
+
     def _prep(self, x):
         assert x.shape == (self.B, 3, self.H, self.W), (tuple(x.shape), (self.B, 3, self.H, self.W))
         return x.to(device=self._dev(), dtype=torch.float32).contiguous()
@@ -195,8 +246,9 @@ class Engine:
         cond = cond.to(device=self._dev(), dtype=torch.float32).contiguous()
         assert cond.shape == (self.B,)
         out = torch.empty((self.B, self.out_channels, self.H, self.W), device=self._dev(), dtype=torch.float32)
-        torch.cuda.current_stream(self._dev()).synchronize()
-        self._check(self.lib.dp_unet_forward(self.h, x.data_ptr(), cond.data_ptr(), out.data_ptr(), None),
+        # enqueued on torch's current stream (stream-ordered with the caller's tensors); the default stream maps to
+        # the blocking NULL-stream contract of the C ABI
+        self._check(self.lib.dp_unet_forward(self.h, x.data_ptr(), cond.data_ptr(), out.data_ptr(), self._stream()),
                     "dp_unet_forward")
         return out
 
@@ -223,12 +275,12 @@ class Engine:
                               init_noise.data_ptr() if init_noise is not None else None,
                               step_noise.data_ptr() if step_noise is not None else None, int(seed),
                               int(sample_offset), anchor.data_ptr() if anchor is not None else None)
-        torch.cuda.current_stream(self._dev()).synchronize()
-        self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), None), "dp_purify")
+        self._keep = (x0, init_noise, step_noise, anchor)    # inputs stay alive until the enqueued work has run
+        self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), self._stream()), "dp_purify")
         return out
 
     OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "attn_small",
-                "softmax_rows", "gn_finalize", "update")
+                "softmax_rows", "update")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

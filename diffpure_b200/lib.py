@@ -80,6 +80,7 @@ SYMBOLS = {
     "dp_version": (C.c_int, []),
     "dp_device_sm_count": (C.c_int, [C.c_void_p]),
     "dp_buffer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "dp_buffer_adopt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "dp_buffer_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "dp_buffer_write": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "dp_buffer_read": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),

@@ -19,6 +19,17 @@ class GuidedDiffusion(PurifyRunner):
         super().__init__()
         self._setup(args, config, device)
         cfg = lowering_adm.cfg_from_reference(config)
+        # The reference builds a SpacedDiffusion from these fields (script_util.py:82-132, respace.py:71-99); this runner
+        # implements the configuration DiffPure ships (configs/imagenet.yml: full 1000-step linear chain, rescaled
+        # timesteps) and refuses anything else instead of silently running a different chain.
+        m = config.model
+        n_steps = int(getattr(m, "diffusion_steps", 1000))
+        if str(getattr(m, "timestep_respacing", "") or "") not in ("", str(n_steps)):
+            raise NotImplementedError(f"timestep_respacing={m.timestep_respacing!r} is not supported (only the full chain)")
+        if getattr(m, "noise_schedule", "linear") != "linear":
+            raise NotImplementedError(f"noise_schedule={m.noise_schedule!r} is not supported (only 'linear')")
+        if not getattr(m, "rescale_timesteps", True):
+            raise NotImplementedError("rescale_timesteps=False is not supported")
         if state_dict is None:
             state_dict = torch.load(f'{model_dir}/256x256_diffusion_uncond.pt', map_location='cpu')
         self.model = ScoreModel("adm", cfg, state_dict, lowering_adm.lower, out_channels=6).eval()

@@ -53,6 +53,11 @@ int dp_device_sm_count(const dp_engine* e);
 
 /* ---- engine-owned device buffers (weights, activations, tables) ------------------------------ */
 int dp_buffer_alloc(dp_engine* e, size_t bytes, int* buf_id);
+/* Registers caller-owned device memory (256-byte aligned, on the engine's device) as an engine buffer without copying:
+ * the packed weight blob is uploaded / NCCL-broadcast once per device and shared by the engines of every batch size
+ * (the reference re-replicates the whole module per forward through nn.DataParallel, eval_sde_adv.py:227-229).
+ * The engine never frees it; it must outlive the engine. */
+int dp_buffer_adopt(dp_engine* e, void* device_ptr, size_t bytes, int* buf_id);
 void* dp_buffer_ptr(dp_engine* e, int buf_id);
 int dp_buffer_write(dp_engine* e, int buf_id, size_t offset, const void* host_src, size_t bytes);
 int dp_buffer_read(dp_engine* e, int buf_id, size_t offset, void* host_dst, size_t bytes);
@@ -166,7 +171,12 @@ int dp_finalize(dp_engine* e, int B, int H, int W);
 
 /* ---- execution ------------------------------------------------------------------------------- */
 
-/* One UNet evaluation: x [B,3,H,W] fp32 (device), cond [B] fp32 (device; DDPM++: 999*t, ADM/ddpm: timestep),
+/* Stream contract of dp_unet_forward / dp_purify: `stream` (a cudaStream_t) != NULL -> all work is enqueued on that
+ * stream, ordered behind what the caller enqueued before, and the call returns without synchronising; `stream` == NULL ->
+ * the call waits for the caller's default-stream work, runs on the engine's private stream and blocks until the result
+ * is complete. Calls on one engine must not overlap (shared run state).
+ *
+ * One UNet evaluation: x [B,3,H,W] fp32 (device), cond [B] fp32 (device; DDPM++: 999*t, ADM/ddpm: timestep),
  * out [B,Cout,H,W] fp32 (device). Mirrors model(x, t) of the reference modules. */
 int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float* out_nchw, void* stream);
 
@@ -195,7 +205,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
- * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 attn_small,7 softmax_rows,8 gn_finalize,9 update,
+ * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 attn_small,7 softmax_rows,8 update,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

@@ -164,7 +164,7 @@ def golden_adm_and_celeba():
     print("celeba tiny |y|", y.abs().mean().item())
 
 
-if __name__ == "__main__" and "--siblings" not in sys.argv:
+if __name__ == "__main__" and "--siblings" not in sys.argv and "--adm-vpsde" not in sys.argv:
     if "--adm-celeba" not in sys.argv:
         main()
     if "--ncsnpp" not in sys.argv:
@@ -200,3 +200,46 @@ def golden_siblings():
 
 if __name__ == "__main__" and "--siblings" in sys.argv:
     golden_siblings()
+
+
+def golden_adm_vpsde():
+    """The canonical ImageNet configuration (run_scripts/imagenet/run_in_rand_inf.sh:12-24: --diffusion_type sde with the
+    default score_type 'guided_diffusion'): the reference's RevVPSDE (runners/diffpure_sde.py:50-147, L101-112 eps -> score
+    with integer timesteps, first 3 of 6 output channels) around the reduced ADM UNet, driven by the Euler shim with
+    injected Brownian increments."""
+    from oracle import adm as A
+    torch.set_grad_enabled(False)
+    m, diffusion, mc = ref_import.build_adm(num_channels=64, image_size=64, num_res_blocks=1)
+    oc = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    sd = weights.make_state_dict(A.param_shapes(oc), seed=5)
+    m.load_state_dict(sd)
+    ref_import.install(euler_shim)
+    from runners.diffpure_sde import RevVPSDE
+    S, B, t_star = 64, 2, 4
+    rev = RevVPSDE(model=m, score_type="guided_diffusion", img_shape=(3, S, S), model_kwargs={})
+    g = torch.Generator().manual_seed(600)
+    x0 = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    e0 = torch.randn(B, 3, S, S, generator=g)
+    steps = OS.num_steps(t_star)
+    z = torch.randn(steps, B, 3, S, S, generator=g)
+    xs = OS.forward_diffuse(x0, e0, t_star)
+    grid = OS.time_grid(t_star)
+    ts = torch.stack([grid[0], grid[-1]])
+    k = {"i": 0}
+
+    def bm(ta, tb):
+        dw = z[k["i"]].reshape(B, -1) * torch.sqrt(tb - ta)
+        k["i"] += 1
+        return dw
+
+    out = euler_shim(rev, xs.reshape(B, -1), ts, bm=bm)[-1].reshape(B, 3, S, S)
+    f0 = rev.f(grid[0], xs.reshape(B, -1)).reshape(B, 3, S, S)
+    g0 = rev.g(grid[0], xs.reshape(B, -1))[:, 0]
+    # x0 / e0 / z are regenerated by the tests from the same seeded generator (adm_vpsde_inputs below)
+    np.savez_compressed(os.path.join(OUT, "adm_tiny_vpsde.npz"), t_star=t_star, loop_out=out.numpy(), f0=f0.numpy(),
+                        g0=g0.numpy(), seed=5, input_seed=600)
+    print("adm tiny VP-SDE: loop |x|", out.abs().mean().item(), "steps", steps, "|f0|", f0.abs().mean().item())
+
+
+if __name__ == "__main__" and "--adm-vpsde" in sys.argv:
+    golden_adm_vpsde()

@@ -103,7 +103,7 @@ def timestep_embedding(timesteps, dim, max_positions=10000):
     """layers.py:515-529 -- [sin | cos], freq_i = exp(-ln(max_pos) * i / (half - 1))."""
     half = dim // 2
     emb = math.log(max_positions) / (half - 1)
-    emb = torch.exp(torch.arange(half, dtype=torch.float32) * -emb)
+    emb = torch.exp(torch.arange(half, dtype=torch.float32, device=timesteps.device) * -emb)
     emb = timesteps.float()[:, None] * emb[None, :]
     return torch.cat([torch.sin(emb), torch.cos(emb)], dim=1)
 

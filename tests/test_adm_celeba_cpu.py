@@ -7,6 +7,8 @@ import torch
 
 from diffpure_b200 import lowering_adm as LA, lowering_ddpm as LD, schedule
 from oracle import adm as A, ddpm_loops as OL, ddpm_unet as D, weights
+from golden_inputs import adm_vpsde_inputs
+from oracle import sde as OS
 from program_interp import Interp
 
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -92,3 +94,33 @@ def test_ddpm_schedules_reproduce_oracle_steps():
     for k in range(3):
         xx = cf[k, 0] * xx + cf[k, 1] * e3 + cf[k, 2] * z
     assert (ref - xx).abs().max().item() < 1e-5
+
+
+def test_adm_on_the_vpsde_path_oracle_and_tables_match_reference_golden():
+    """The canonical ImageNet configuration (--diffusion_type sde, score_type 'guided_diffusion'): the fixture was produced
+    by the reference's RevVPSDE around its own ADM UNet (runners/diffpure_sde.py:101-112,131-147)."""
+    d = load("adm_tiny_vpsde.npz")
+    t_star = int(d["t_star"])
+    sd = weights.make_state_dict(A.param_shapes(ADM_TINY), seed=int(d["seed"]))
+    unet = lambda x, t: A.forward(ADM_TINY, sd, x, t)  # noqa: E731
+    x0, e0, z = adm_vpsde_inputs(d["input_seed"], t_star)
+    with torch.no_grad():
+        out = OS.purify_sde(unet, x0, t_star, e0, z, score_type="guided_diffusion")
+        xs = OS.forward_diffuse(x0, e0, t_star)
+        grid = OS.time_grid(t_star)
+        f0 = OS.rev_vpsde_f(unet, "guided_diffusion", grid[0], xs)
+    assert (out - d["loop_out"]).abs().max().item() < 1e-4
+    assert (f0 - d["f0"]).abs().max().item() < 1e-4
+    assert (OS.rev_vpsde_g(grid[0], 2) - d["g0"]).abs().max().item() < 1e-6
+    # the engine's per-step tables (cond = floor(fp32(s * 1000)), c0, c1, c2) replay the same trajectory
+    cond, coef = schedule.vpsde_tables(t_star, "guided_diffusion")
+    assert cond.tolist() == [float(int(v)) for v in cond.tolist()] and len(cond) == OS.num_steps(t_star)
+    xx = xs
+    with torch.no_grad():
+        for k in range(len(cond)):
+            eps = unet(xx, torch.full((2,), int(cond[k])))[:, :3]
+            xx = float(coef[k, 0]) * xx + float(coef[k, 1]) * eps + float(coef[k, 2]) * z[k]
+    assert (xx - d["loop_out"]).abs().max().item() < 1e-4
+    # ... and the 150-step ImageNet grid starts at 149 with one duplicate (SURVEY appendix A.5)
+    c150, _ = schedule.vpsde_tables(150, "guided_diffusion")
+    assert len(c150) == 150 and c150[0] == 149 and c150[-1] == 1 and len(set(c150.tolist())) == 149

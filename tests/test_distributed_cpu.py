@@ -22,6 +22,25 @@ def _worker(rank, world, port, ret):
         full = torch.arange(10 * 3, dtype=torch.float32).reshape(10, 3)
         gathered = D.gather_shards(full[s:e], world)          # equal shards: 5 + 5
         ok = ok and torch.equal(gathered, full)
+        s, e = D.shard_range(11, rank, world)                 # ragged shards: 6 + 5, padded for the collective
+        full11 = torch.arange(11 * 3, dtype=torch.float32).reshape(11, 3)
+        ok = ok and torch.equal(D.gather_shards(full11[s:e], world, total=11), full11)
+        # packed weight blob: rank 0 packs the real constants, rank 1 only the layout; ONE broadcast of the bytes
+        from diffpure_b200 import lowering_ncsnpp as L, synthetic
+        from diffpure_b200.engine import WeightBlob
+        from types import SimpleNamespace
+        cfg = SimpleNamespace(image_size=16, num_channels=3, nf=64, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(8,))
+        shapes = L.param_shapes(cfg)
+        real = synthetic.random_state_dict(shapes, seed=4)
+        sd = real if rank == 0 else {k: torch.zeros(v) for k, v in shapes.items()}
+        prog = L.lower(cfg, sd, 2)
+        blob = D.broadcast_blob(WeightBlob(prog, "cpu", upload=(rank == 0)), src=0)
+        want = L.lower(cfg, real, 2)
+        for t in want.tensors:
+            if t.init is not None:
+                ref_t = t.init.to(torch.bfloat16).float() if t.dtype == "bf16" else t.init.float()
+                ok = ok and torch.equal(blob.tensor(t.name, t.dtype), ref_t.reshape(-1))
+        ok = ok and blob.matches(L.lower(cfg, real, 5))       # the layout does not depend on the batch size
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

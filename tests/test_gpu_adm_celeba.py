@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import adm as A, ddpm_unet as D, weights
+from golden_inputs import ADM_TINY_REF_CONFIG, adm_vpsde_inputs
+from oracle import adm as A, ddpm_unet as D, sde as OS, weights
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -115,3 +116,111 @@ def test_full_size_256_eval_vs_oracle(which):
     eng.close()
     assert n_pair > 0
     assert rel(yg, y) < TOL_EVAL, rel(yg, y)
+
+
+def test_adm_on_the_vpsde_path_runner_golden():
+    """The canonical ImageNet configuration (run_scripts/imagenet/run_in_rand_inf.sh:12-24: --diffusion_type sde, default
+    score_type 'guided_diffusion'): RevGuidedDiffusion(dataset='ImageNet') on the engine vs the fixture produced by the
+    reference's RevVPSDE around its own ADM UNet (runners/diffpure_sde.py:101-112,160-170)."""
+    from diffpure_b200.runners.diffpure_sde import RevGuidedDiffusion
+    d = load("adm_tiny_vpsde.npz")
+    t_star = int(d["t_star"])
+    x0, e0, z = adm_vpsde_inputs(d["input_seed"], t_star)
+    acfg = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    sd = weights.make_state_dict(A.param_shapes(acfg), seed=int(d["seed"]))
+    args = SimpleNamespace(t=t_star, rand_t=False, t_delta=15, use_bm=False, score_type="guided_diffusion",
+                           sample_step=1, log_dir="/tmp/dp_test_logs", save_images=False)
+    config = SimpleNamespace(data=SimpleNamespace(dataset="ImageNet"), model=SimpleNamespace(**ADM_TINY_REF_CONFIG))
+    r = RevGuidedDiffusion(args, config, device=torch.device("cuda:0"), state_dict=sd)
+    with torch.no_grad():
+        out = r.image_editing_sample(x0.cuda(), bs_id=3, tag="x", init_noise=e0.cuda(), step_noise=z.cuda()).cpu()
+    assert out.shape == (2, 3, 64, 64)
+    assert rel(out, d["loop_out"]) < TOL_TRAJ, rel(out, d["loop_out"])
+    # the SDE-object protocol on the same engine: f at the first grid point vs the reference's
+    xs = OS.forward_diffuse(x0, e0, t_star)
+    f0 = r.rev_vpsde.f(OS.time_grid(t_star)[0].cuda(), xs.cuda().reshape(2, -1)).reshape(2, 3, 64, 64).cpu()
+    assert rel(f0, d["f0"]) < TOL_EVAL, rel(f0, d["f0"])
+    r.model.release()
+
+
+@pytest.mark.parametrize("which", ["adm_vpsde", "adm_guided", "celeba"])
+def test_full_size_256_three_step_chain_vs_oracle(which):
+    """BASELINE-size 256x256 models, 3 steps of the real schedule (the first three of the 150- / 100-step chains) at B=1
+    with injected noise vs the CPU oracle loop."""
+    from diffpure_b200 import lib, schedule, synthetic
+    from diffpure_b200.engine import Engine
+    from oracle import ddpm_loops as OL
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    e0 = torch.randn(1, 3, 256, 256, generator=g)
+    z = torch.randn(3, 1, 3, 256, 256, generator=g)
+    if which.startswith("adm"):
+        from diffpure_b200 import lowering_adm as L
+        cfg, ocfg = L.imagenet_cfg(), A.IMAGENET_CFG
+        sd = synthetic.random_state_dict(L.param_shapes(cfg), seed=0)
+        unet = lambda x, t: A.forward(ocfg, sd, x, t)  # noqa: E731
+    else:
+        from diffpure_b200 import lowering_ddpm as L
+        cfg, ocfg = L.celeba_cfg(), D.CELEBA_CFG
+        sd = synthetic.random_state_dict(L.param_shapes(cfg), seed=0)
+        unet = lambda x, t: D.forward(ocfg, sd, x, t)  # noqa: E731
+    with torch.no_grad():
+        if which == "adm_vpsde":
+            t_star = 150
+            cond, coef = schedule.vpsde_tables(t_star, "guided_diffusion")
+            sx, se = schedule.vpsde_forward_scales(t_star)
+            kind = lib.DP_UPDATE_LINEAR
+            grid = OS.time_grid(t_star)
+            x = OS.forward_diffuse(x0, e0, t_star)
+            for k in range(3):
+                t, h = grid[k], grid[k + 1] - grid[k]
+                x = x + OS.rev_vpsde_f(unet, "guided_diffusion", t, x) * h + \
+                    OS.rev_vpsde_g(t, 1)[:, None, None, None] * z[k] * torch.sqrt(h)
+        elif which == "adm_guided":
+            cond, coef, sx, se = schedule.guided_tables(150)
+            kind = lib.DP_UPDATE_LEARNED_RANGE
+            tab = OL.GuidedTables()
+            x = sx * x0 + se * e0
+            for k in range(3):
+                x = OL.guided_p_sample(unet, tab, x, 149 - k, z[k])
+        else:
+            cond, coef, sx, se = schedule.ddpm_tables(100)
+            kind = lib.DP_UPDATE_LINEAR
+            x = sx * x0 + se * e0
+            for k in range(3):
+                eps = unet(x, torch.tensor([99 - k]))
+                x = float(coef[k, 0]) * x + float(coef[k, 1]) * eps + float(coef[k, 2]) * z[k]
+    eng = Engine(L.lower(cfg, sd, 1), device=0)
+    out = eng.purify(x0.cuda(), cond[:3], coef[:3], sx, se, update_kind=kind, init_noise=e0.cuda(),
+                     step_noise=z.cuda()).cpu()
+    eng.close()
+    assert rel(out, x) < TOL_TRAJ, rel(out, x)
+
+
+@pytest.mark.parametrize("which,B", [("adm", 32), ("celeba", 16)])
+def test_full_size_256_benchmark_batch_matches_b1_engine(which, B):
+    """At the benchmarked batch (ADM 32, CelebA 16) the tile choices differ from B=1 (CTA pairs everywhere, BN=256):
+    3 steps of the chain at batch B vs the same samples through B=1 engines -- same arithmetic, different tiling."""
+    from diffpure_b200 import lib, schedule, synthetic
+    from diffpure_b200.engine import Engine
+    if which == "adm":
+        from diffpure_b200 import lowering_adm as L
+        cfg = L.imagenet_cfg()
+        cond, coef = schedule.vpsde_tables(150, "guided_diffusion")
+        sx, se = schedule.vpsde_forward_scales(150)
+    else:
+        from diffpure_b200 import lowering_ddpm as L
+        cfg = L.celeba_cfg()
+        cond, coef, sx, se = schedule.ddpm_tables(100)
+    sd = synthetic.random_state_dict(L.param_shapes(cfg), seed=0)
+    g = torch.Generator().manual_seed(22)
+    x0 = torch.rand(B, 3, 256, 256, generator=g) * 2 - 1
+    engB = Engine(L.lower(cfg, sd, B), device=0)
+    big = engB.purify(x0.cuda(), cond[:3], coef[:3], sx, se, seed=5, sample_offset=0).cpu()
+    engB.close()
+    eng1 = Engine(L.lower(cfg, sd, 1), device=0)
+    for i in (0, B - 1):
+        one = eng1.purify(x0[i:i + 1].cuda(), cond[:3], coef[:3], sx, se, seed=5, sample_offset=i).cpu()
+        assert rel(big[i:i + 1], one) < 1e-3, (i, rel(big[i:i + 1], one))
+    eng1.close()
+    assert torch.isfinite(big).all()

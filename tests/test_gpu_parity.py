@@ -51,7 +51,7 @@ def test_unet_eval_cifar10_golden():
     sd = weights.make_state_dict(O.param_shapes(O.CIFAR10_CFG), seed=int(d["seed"]))
     eng = engine_for(O.CIFAR10_CFG, sd, d["x"].shape[0])
     y = eng.unet_forward(d["x"].cuda(), d["labels"].cuda()).cpu()
-    assert eng.launches_per_eval == 534   # 203 GEMMs + 163 x (gn_finalize + gn_apply) + conv_in, stats, update, embed, attn_small
+    assert eng.launches_per_eval == 371   # 203 GEMMs + 163 gn_apply + conv_in, stats, update, embed, attn_small
     eng.close()
     assert rel(y, d["y"]) < TOL_EVAL, rel(y, d["y"])
 
@@ -154,7 +154,6 @@ def test_determinism_and_shard_invariance():
 def test_full_size_identity_update_property():
     """BASELINE batch (512 images): with update coefficients (1, 0, 0) the loop must return exactly the
     forward-diffused input whatever the UNet computes -- exercises the full-size buffers, graph and layouts."""
-    cfg = O.CIFAR10_CFG
     from diffpure_b200 import lowering_ncsnpp as L, synthetic
     from diffpure_b200.engine import Engine
     sd = synthetic.random_state_dict(L.param_shapes(L.cifar10_cfg()), seed=0)
@@ -166,12 +165,50 @@ def test_full_size_identity_update_property():
     cond = np.full(2, 50.0, np.float32)
     coef = np.tile(np.array([[1.0, 0.0, 0.0]], np.float32), (2, 1))
     out = eng.purify(x0.cuda(), cond, coef, 0.75, 0.5, init_noise=e0.cuda()).cpu()
-    y = eng.unet_forward(x0.cuda(), torch.full((B,), 50.0).cuda()).cpu()
-    eng.close()
+    labels = torch.full((B,), 50.0).cuda()
+    y = eng.unet_forward(x0.cuda(), labels).cpu()
     assert torch.equal(out, 0.75 * x0 + 0.5 * e0)
     assert torch.isfinite(y).all() and y.std().item() > 0.05
-    # per-sample independence: every image's output depends on that image only
-    assert torch.allclose(y[0], y[0])
+    # per-sample independence at the benchmarked batch: perturbing samples 1 and 300 leaves every other sample's output
+    # bit-identical (no cross-sample coupling, no atomics) and changes those two
+    x1 = x0.clone()
+    x1[1] += 0.25
+    x1[300] = -x1[300]
+    y1 = eng.unet_forward(x1.cuda(), labels).cpu()
+    eng.close()
+    keep = torch.ones(B, dtype=torch.bool)
+    keep[1] = keep[300] = False
+    assert torch.equal(y1[keep], y[keep])
+    assert not torch.equal(y1[1], y[1]) and not torch.equal(y1[300], y[300])
+
+
+def test_full_model_100_step_trajectory_at_pair_tile_batch():
+    """The benchmarked loop shape: all 100 Euler-Maruyama steps from t*=0.1 on the full CIFAR-10 model at B=96 (the 32x32 and
+    16x16 convolutions run on CTA-pair tiles, as at B=512) with injected noise; the first two samples are held to the
+    oracle loop. The measured rel-L2 is reported, not just bounded (stated bound: 5e-3 for K <= 100)."""
+    from diffpure_b200 import schedule
+    cfg = O.CIFAR10_CFG
+    sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
+    g = torch.Generator().manual_seed(6)
+    B, t_star = 96, 100
+    steps = OS.num_steps(t_star)
+    assert steps == 100
+    x0 = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
+    e0 = torch.randn(B, 3, 32, 32, generator=g)
+    z = torch.randn(steps, B, 3, 32, 32, generator=g)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = OS.purify_sde(lambda xx, tt: O.forward(cfg, sd, xx, tt), x0[:2], t_star, e0[:2], z[:, :2])
+    cond, coef = schedule.vpsde_tables(t_star)
+    sx, se = schedule.vpsde_forward_scales(t_star)
+    eng = engine_for(cfg, sd, B)
+    assert eng.pair_gemms >= 40
+    out = eng.purify(x0.cuda(), cond, coef, sx, se, init_noise=e0.cuda(), step_noise=z.cuda()).cpu()
+    eng.close()
+    r = rel(out[:2], ref)
+    print(f"100-step trajectory at B=96 (pair tiles): rel-L2 of the state vs the oracle loop = {r:.3e}")
+    assert r < TOL_TRAJ, r
+    assert torch.isfinite(out).all()
 
 
 def test_runner_api_matches_engine():
