@@ -84,16 +84,36 @@ int launch_embed(const EmbedParams& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm: streaming apply; every CTA first folds its sample's partial statistics into per-channel scale / shift
+// GroupNorm: finalize (per sample: partial sums -> per-channel scale / shift) + streaming apply
 // ------------------------------------------------------------------------------------------------
-// y = x * scale + shift folds mean, rstd, gamma, beta and FiLM. The partial sums of one sample are at most 16 rows of
-// C float2 (longer lists are collapsed once by stats_reduce), all L2 hits: re-deriving them per CTA costs less than the
-// separate one-CTA-per-sample finalize launch it replaces (163 launches of ~10 us per DDPM++ evaluation) and the loads
-// overlap the CTA's own data loads, which are issued first. Summation order is fixed -> bit-reproducible.
-__device__ __forceinline__ void gn_fold_stats(const GnParams& p, int b, float* sc, float* sh, float* gs) {
+// ss layout: [B][2][C] fp32 (scale[C] then shift[C]); y = x * scale + shift folds mean, rstd, gamma, beta and FiLM.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(GnParams p, float* __restrict__ ss) {
+  pdl_entry();
+  extern __shared__ float sm[];
   const int C = p.C0 + p.C1;
   const int G = p.groups;
+  float* sc = sm;
+  float* sh = sm + C;
+  float* gs = sm + 2 * C;
+  const int b = blockIdx.x;
   const int tid = threadIdx.x;
+  const int HW = p.H * p.W;
+  // affine / FiLM parameters do not depend on the statistics: fetch them first so their latency overlaps the partial sums
+  // (C <= 2 * blockDim.x for every UNet here; further channels are fetched in the last loop)
+  float pg[2], pb[2], pfs[2], pfb[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * 256;
+    pg[i] = pb[i] = pfs[i] = pfb[i] = 0.f;
+    if (c < C) {
+      pg[i] = __ldg(p.gamma + c);
+      pb[i] = __ldg(p.beta + c);
+      if (p.film) {
+        pfs[i] = __ldg(p.film + static_cast<size_t>(b) * p.film_ld + c);
+        pfb[i] = __ldg(p.film + static_cast<size_t>(b) * p.film_ld + C + c);
+      }
+    }
+  }
   for (int c = tid; c < C; c += blockDim.x) {
     const float* st;
     int P, Cx, cl;
@@ -124,7 +144,6 @@ __device__ __forceinline__ void gn_fold_stats(const GnParams& p, int b, float* s
   }
   __syncthreads();
   const int cpg = C / G;
-  const int HW = p.H * p.W;
   for (int g = tid; g < G; g += blockDim.x) {
     double S = 0.0, Q = 0.0;
     for (int j = 0; j < cpg; ++j) {
@@ -139,15 +158,39 @@ __device__ __forceinline__ void gn_fold_stats(const GnParams& p, int b, float* s
     gs[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
   }
   __syncthreads();
+  for (int c = tid, i = 0; c < C; c += blockDim.x, ++i) {
+    const int g = c / cpg;
+    float gam, bet, fsv = 0.f, fbv = 0.f;
+    if (i < 2) { gam = pg[i]; bet = pb[i]; fsv = pfs[i]; fbv = pfb[i]; }
+    else {
+      gam = p.gamma[c]; bet = p.beta[c];
+      if (p.film) { fsv = p.film[static_cast<size_t>(b) * p.film_ld + c]; fbv = p.film[static_cast<size_t>(b) * p.film_ld + C + c]; }
+    }
+    float a = gam * gs[2 * g + 1];
+    float bb = bet - gs[2 * g] * a;
+    if (p.film) {
+      const float fs = 1.0f + fsv;
+      a *= fs;
+      bb = bb * fs + fbv;
+    }
+    ss[(static_cast<size_t>(b) * 2) * C + c] = a;
+    ss[(static_cast<size_t>(b) * 2 + 1) * C + c] = bb;
+  }
+}
+
+int launch_gn_finalize(const GnParams& p, float* ss, cudaStream_t s) {
+  const int C = p.C0 + p.C1;
+  const size_t smem = static_cast<size_t>(2 * C + 2 * p.groups) * sizeof(float);
+  (void)launch_k(gn_finalize_kernel, dim3(p.B), dim3(256), smem, s, 1, p, ss);
+  return static_cast<int>(cudaGetLastError());
 }
 
 // Streaming apply: plain large grid (measured 5.9-6.1 TB/s for this access shape vs 3.7 TB/s for a persistent loop,
 // tools/bench_stream.cu). One CTA = U*rpi output pixels of one sample; scale/shift of the sample staged in smem;
 // every thread owns one fixed 8-channel vector and issues all its loads before any compute / store.
 template <int RES, bool SRC16, int U>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p, const float* __restrict__ ss) {
   pdl_entry();
-  extern __shared__ float gsm[];  // [C] channel sums, [C] channel sums of squares, [2 G] group mean / rstd
   const int C = p.C0 + p.C1;
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -199,38 +242,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
       }
     }
   }
-  // per-channel scale / shift of this thread's 8 channels from the sample's partial statistics (folded per CTA, behind
-  // the data loads issued above)
+  // per-channel scale / shift of this sample: 4 x 16-byte loads per thread straight from L1/L2 (all CTAs resident
+  // on an SM work on the same few samples); issued right behind the data loads, no barrier in the kernel
   float a8[8], b8[8];
-  if (p.stats0 != nullptr) {
-    float* gs = gsm + 2 * C;
-    gn_fold_stats(p, b, gsm, gsm + C, gs);
-    const int cpg = C / p.groups;
-    const float4* g4 = reinterpret_cast<const float4*>(p.gamma + c);
-    const float4* t4 = reinterpret_cast<const float4*>(p.beta + c);
-    const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), ta = __ldg(t4), tb = __ldg(t4 + 1);
-    const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-    const float bet[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      const float a = gam[j] * gs[2 * g + 1];
-      a8[j] = a;
-      b8[j] = bet[j] - gs[2 * g] * a;
-    }
-    if (p.film) {
-      const float4* fs4 = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(b) * p.film_ld + c);
-      const float4* fb4 = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(b) * p.film_ld + C + c);
-      const float4 sa = __ldg(fs4), sb = __ldg(fs4 + 1), ba = __ldg(fb4), bb = __ldg(fb4 + 1);
-      const float fsv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-      const float fbv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float fs = 1.0f + fsv[j];
-        a8[j] *= fs;
-        b8[j] = b8[j] * fs + fbv[j];
-      }
-    }
+  if (ss != nullptr) {
+    const float4* qa = reinterpret_cast<const float4*>(ss + static_cast<size_t>(b) * 2 * C + c);
+    const float4* qb = reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * 2 + 1) * C + c);
+    const float4 a0 = __ldg(qa), a1 = __ldg(qa + 1), b0 = __ldg(qb), b1 = __ldg(qb + 1);
+    a8[0] = a0.x; a8[1] = a0.y; a8[2] = a0.z; a8[3] = a0.w; a8[4] = a1.x; a8[5] = a1.y; a8[6] = a1.z; a8[7] = a1.w;
+    b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a8[j] = 1.f; b8[j] = 0.f; }
@@ -286,7 +306,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
   }
 }
 
-int launch_gn_apply(const GnParams& p, int num_sms, cudaStream_t s) {
+int launch_gn_apply(const GnParams& p, const float* ss, int num_sms, cudaStream_t s) {
   (void)num_sms;
   const int C = p.C0 + p.C1;
   const int vpp = C / 8;
@@ -302,16 +322,16 @@ int launch_gn_apply(const GnParams& p, int num_sms, cudaStream_t s) {
   static const int u_big = [] { const char* v = std::getenv("DP_GN_U"); return v ? std::atoi(v) : 4; }();
   const int U = p.resample == 2 ? 1 : ((p.resample == 0 && HWo >= 256 && u_big >= 4) ? 4 : 2);
   const dim3 grid((HWo + U * rpi - 1) / (U * rpi), p.B);
-  const size_t smem = p.stats0 ? static_cast<size_t>(2 * C + 2 * p.groups) * sizeof(float) : 0;
+  const size_t smem = 0;
   if (p.src0h != nullptr) {
     if (p.resample != 0 || p.C1 != 0) return static_cast<int>(cudaErrorInvalidValue);
-    if (U == 4) (void)launch_k(gn_apply_kernel<0, true, 4>, dim3(grid), dim3(threads), smem, s, 1, p);
-    else (void)launch_k(gn_apply_kernel<0, true, 2>, dim3(grid), dim3(threads), smem, s, 1, p);
+    if (U == 4) (void)launch_k(gn_apply_kernel<0, true, 4>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+    else (void)launch_k(gn_apply_kernel<0, true, 2>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
   } else if (p.resample == 0) {
-    if (U == 4) (void)launch_k(gn_apply_kernel<0, false, 4>, dim3(grid), dim3(threads), smem, s, 1, p);
-    else (void)launch_k(gn_apply_kernel<0, false, 2>, dim3(grid), dim3(threads), smem, s, 1, p);
-  } else if (p.resample == 1) (void)launch_k(gn_apply_kernel<1, false, 2>, dim3(grid), dim3(threads), smem, s, 1, p);
-  else (void)launch_k(gn_apply_kernel<2, false, 1>, dim3(grid), dim3(threads), smem, s, 1, p);
+    if (U == 4) (void)launch_k(gn_apply_kernel<0, false, 4>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+    else (void)launch_k(gn_apply_kernel<0, false, 2>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  } else if (p.resample == 1) (void)launch_k(gn_apply_kernel<1, false, 2>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
+  else (void)launch_k(gn_apply_kernel<2, false, 1>, dim3(grid), dim3(threads), smem, s, 1, p, ss);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -472,6 +492,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
       xn = mean + k[6] * expf(0.5f * logvar) * z;
     }
     *xp = xn;
+    if (cp.states) cp.states[((static_cast<size_t>(step + 1) * p.B + b) * 3 + c) * HW + pix] = xn;
   }
 }
 

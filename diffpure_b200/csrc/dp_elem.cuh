@@ -32,9 +32,13 @@ struct GnParams {
   int B, H, W, groups; float eps; int silu; int resample;
   __nv_bfloat16* out; __nv_bfloat16* raw; float* raw_f32;
 };
-// Streaming normalise (+SiLU, FiLM, resample, concat) -> bf16; every CTA folds its sample's partial statistics into the
-// per-channel scale / shift itself. `stats0 == nullptr` = identity (cast / resample only).
-int launch_gn_apply(const GnParams& p, int num_sms, cudaStream_t s);
+// finalize: partial statistics -> ss [B][2][C] (scale, shift); apply: streaming normalise (+SiLU, resample) -> bf16.
+// `ss == nullptr` in apply = identity (cast / resample only).
+// (Folding the finalize into every apply CTA was measured in round 2: 163 fewer launches per DDPM++ evaluation, but the
+//  redundant per-CTA fold -- 16 CTAs per sample, two barriers and a double-precision group reduction in front of the
+//  streaming part -- cost 11.0 ms instead of 7.0 + 1.7 ms per evaluation at B=512; the two-kernel form stays.)
+int launch_gn_finalize(const GnParams& p, float* ss, cudaStream_t s);
+int launch_gn_apply(const GnParams& p, const float* ss, int num_sms, cudaStream_t s);
 
 // fp32 [B, HW, C] -> per-channel partial (sum, sumsq) [B][P][C][2], P = ceil(HW / 128)
 int launch_stats(const float* src, float* stats, int B, int HW, int C, cudaStream_t s);
@@ -52,6 +56,7 @@ struct CallParams {
   const float* step_noise;  // [steps,B,3,H,W] standard normals, or null -> counter-based generator
   unsigned long long seed, sample_offset;
   int update_kind;  // 0: x <- k0 x + k1 eps + k2 z ; 1: learned-range DDPM step ; 2: kind 0 + k3 x_init
+  float* states;    // optional [steps+1,B,3,H,W] NCHW: the update of step k also stores the new state at index k+1
 };
 
 // Per-step update from an fp32 eps buffer [B*H*W, ld] (written by the output conv run as a tensor-core GEMM):
@@ -76,6 +81,35 @@ int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nh
                       cudaStream_t s);
 int launch_nhwc_to_nchw(const float* x_nhwc, float* out_nchw, int B, int C, int HW, cudaStream_t s);
 int launch_step_advance(int* step, cudaStream_t s);
+
+// ---- data-gradient kernels (dp_bwd.cu) ---------------------------------------------------------------------------------
+// GroupNorm(+SiLU, +resample, +concat) backward. Sources / statistics as in GnParams (the forward tensors);
+// g: dL/d(output), fp32 NHWC at the forward OUTPUT resolution with C0+C1 channels.
+struct GnBwdParams {
+  const float* src0; const __nv_bfloat16* src0h; const float* stats0; int C0, P0;
+  const float* src1; const float* stats1; int C1, P1;
+  const float* gamma; const float* beta;
+  int B, H, W, groups; float eps; int silu; int resample;
+  const float* g;
+  const float* add0; float add0_scale;  // optional fp32 at the output resolution, C0+C1 channels: d += scale * resample^T(add0)
+  const float* add1;                    // optional fp32 [B,H,W,C0]: added to the first source's gradient (skip connection)
+  float* part;                          // scratch [B][ceil(HW/128)][C0+C1][2]
+  float* d0_f32; __nv_bfloat16* d0_bf16;  // gradient wrt source 0 [B,H,W,C0]
+  float* d1_f32;                          // gradient wrt source 1 [B,H,W,C1]
+};
+int launch_gn_bwd(const GnBwdParams& p, cudaStream_t s);
+int launch_softmax_bwd(const __nv_bfloat16* pnum, const float* rowsum, const float* dp_, __nv_bfloat16* ds,
+                       __nv_bfloat16* pn, long long rows, int T, cudaStream_t s);
+struct TransposeParams {
+  const __nv_bfloat16* in; __nv_bfloat16* out; int rows, cols, ld_in, ld_out, batch;
+  long long in_batch_stride, out_batch_stride;
+};
+int launch_transpose(const TransposeParams& p, cudaStream_t s);
+struct AttnSmallBwdParams {
+  const __nv_bfloat16* qkv; const __nv_bfloat16* go; __nv_bfloat16* out; int B, T, heads, d; float scale;
+};
+int launch_attn_small_bwd(const AttnSmallBwdParams& p, cudaStream_t s);
+int launch_grad_in(const float* g_nchw, __nv_bfloat16* out, int B, int C, int HW, int Cpad, cudaStream_t s);
 
 // Counter-based standard normal: Philox4x32-10 keyed by seed, counter (sample, step+1 | 0 = init, pixel),
 // Box-Muller on the four outputs; component c in [0,3).

@@ -19,7 +19,8 @@ namespace {
 
 std::string g_create_error;
 
-enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX, OP_UPDATE };
+enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX, OP_UPDATE,
+              OP_GN_BWD, OP_SOFTMAX_BWD, OP_TRANSPOSE, OP_ATTN_SMALL_BWD, OP_GRAD_IN, OP_GN_FINALIZE };
 
 struct StatsReduce {
   const float* in;
@@ -48,6 +49,11 @@ struct Op {
   dp::AttnSmallParams attn;
   dp_softmax_desc smax;
   dp::UpdateParams upd;
+  dp::GnBwdParams gnb;
+  dp_softmax_bwd_desc smb;
+  dp::TransposeParams tr;
+  dp::AttnSmallBwdParams attnb;
+  dp_grad_in_desc gin;
 };
 
 }  // namespace
@@ -68,6 +74,12 @@ struct dp_engine {
   float* x_init = nullptr;           // copy of the initial state (anchor of the Langevin-dynamics update)
   float* eps_out = nullptr;          // NCHW fp32 [B,Cout,H,W]
   float* cond_per_sample = nullptr;  // [B]
+  float* g_in = nullptr;             // NCHW fp32 [B,Cg,H,W]: dL/d(UNet output) of dp_unet_vjp
+  int g_in_channels = 0;
+  float* gn_ss = nullptr;            // [B][2][C] scale/shift scratch shared by all GroupNorm ops (stream-ordered)
+  size_t gn_ss_floats = 0;
+  float* bwd_part = nullptr;         // scratch of the GroupNorm backward partial sums (stream-ordered, shared by all ops)
+  size_t bwd_part_floats = 0;
   int* d_step = nullptr;
   float* d_cond = nullptr;
   float* d_coef = nullptr;
@@ -143,7 +155,10 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s, op.cg);
       break;
     case OP_GN:
-      rc = dp::launch_gn_apply(op.gn, e->num_sms, s);
+      rc = dp::launch_gn_apply(op.gn, op.gn.stats0 ? e->gn_ss : nullptr, e->num_sms, s);
+      break;
+    case OP_GN_FINALIZE:
+      rc = dp::launch_gn_finalize(op.gn, e->gn_ss, s);
       break;
     case OP_STATS:
       rc = dp::launch_stats(op.stats.src, op.stats.stats, op.stats.B, op.stats.HW, op.stats.C, s);
@@ -170,6 +185,27 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       rc = dp::launch_update(u, s);
       break;
     }
+    case OP_GN_BWD: {
+      dp::GnBwdParams g = op.gnb;
+      g.part = e->bwd_part;
+      rc = dp::launch_gn_bwd(g, s);
+      break;
+    }
+    case OP_SOFTMAX_BWD:
+      rc = dp::launch_softmax_bwd(static_cast<const __nv_bfloat16*>(op.smb.pnum_bf16), op.smb.rowsum, op.smb.dp,
+                                  static_cast<__nv_bfloat16*>(op.smb.ds_bf16), static_cast<__nv_bfloat16*>(op.smb.pn_bf16),
+                                  op.smb.rows, op.smb.T, s);
+      break;
+    case OP_TRANSPOSE:
+      rc = dp::launch_transpose(op.tr, s);
+      break;
+    case OP_ATTN_SMALL_BWD:
+      rc = dp::launch_attn_small_bwd(op.attnb, s);
+      break;
+    case OP_GRAD_IN:
+      rc = dp::launch_grad_in(e->g_in, static_cast<__nv_bfloat16*>(op.gin.out_bf16), op.gin.B, op.gin.C,
+                              op.gin.H * op.gin.W, op.gin.Cpad, s);
+      break;
     case OP_SOFTMAX:
       rc = dp::launch_softmax_rows(op.smax.src, static_cast<__nv_bfloat16*>(op.smax.out_bf16), op.smax.rows,
                                    op.smax.T, s);
@@ -273,6 +309,9 @@ void dp_destroy(dp_engine* e) {
   cudaFree(e->x_init);
   cudaFree(e->eps_out);
   cudaFree(e->cond_per_sample);
+  cudaFree(e->g_in);
+  cudaFree(e->gn_ss);
+  cudaFree(e->bwd_part);
   cudaFree(e->d_step);
   cudaFree(e->d_cond);
   cudaFree(e->d_coef);
@@ -512,6 +551,19 @@ int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d) {
     e->ops.push_back(r);
     if (which) { p.stats1 = r.sred.out; p.P1 = 1; } else { p.stats0 = r.sred.out; p.P0 = 1; }
   }
+  if (p.stats0) {
+    const size_t need = static_cast<size_t>(d->B) * 2 * C;
+    if (need > e->gn_ss_floats) {  // ops read the pointer from the engine at launch time: growing it here is safe
+      cudaFree(e->gn_ss);
+      e->gn_ss = nullptr;
+      DP_CUDA(e, cudaMalloc(&e->gn_ss, need * sizeof(float)));
+      e->gn_ss_floats = need;
+    }
+    Op f;
+    f.kind = OP_GN_FINALIZE;
+    f.gn = p;
+    e->ops.push_back(f);
+  }
   Op op;
   op.kind = OP_GN;
   op.gn = p;
@@ -571,6 +623,87 @@ int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d) {
   return DP_OK;
 }
 
+int dp_op_gn_bwd(dp_engine* e, const dp_gn_bwd_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  const int C = d->C0 + d->C1;
+  if (C <= 0 || C % d->groups || !d->stats0 || !d->g) return fail(e, DP_ERR_INVALID, "gn_bwd: channels / statistics / gradient");
+  if (d->C1 && (!d->src1 || !d->stats1 || !d->d1_f32)) return fail(e, DP_ERR_INVALID, "gn_bwd: second source incomplete");
+  if (d->resample && (d->H % 2 || d->W % 2) && d->resample == 2) return fail(e, DP_ERR_INVALID, "gn_bwd: odd grid");
+  Op op;
+  op.kind = OP_GN_BWD;
+  dp::GnBwdParams& p = op.gnb;
+  std::memset(&p, 0, sizeof(p));
+  if (d->src0_is_bf16) p.src0h = reinterpret_cast<const __nv_bfloat16*>(d->src0);
+  else p.src0 = d->src0;
+  p.stats0 = d->stats0; p.C0 = d->C0; p.P0 = d->P0;
+  p.src1 = d->src1; p.stats1 = d->stats1; p.C1 = d->C1; p.P1 = d->P1;
+  p.gamma = d->gamma; p.beta = d->beta;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.groups = d->groups; p.eps = d->eps; p.silu = d->silu; p.resample = d->resample;
+  p.g = d->g; p.add0 = d->add0; p.add0_scale = d->add0_scale; p.add1 = d->add1;
+  p.d0_f32 = d->d0_f32; p.d0_bf16 = static_cast<__nv_bfloat16*>(d->d0_bf16); p.d1_f32 = d->d1_f32;
+  const size_t need = static_cast<size_t>(d->B) * ((d->H * d->W + 127) / 128) * C * 2;
+  if (need > e->bwd_part_floats) {   // ops read the pointer from the engine at launch time: growing it here is safe
+    DP_CUDA(e, cudaSetDevice(e->device));
+    cudaFree(e->bwd_part);
+    e->bwd_part = nullptr;
+    DP_CUDA(e, cudaMalloc(&e->bwd_part, need * sizeof(float)));
+    e->bwd_part_floats = need;
+  }
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_softmax_bwd(dp_engine* e, const dp_softmax_bwd_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  Op op;
+  op.kind = OP_SOFTMAX_BWD;
+  op.smb = *d;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_transpose(dp_engine* e, const dp_transpose_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->batch <= 0 || d->batch > 65535) return fail(e, DP_ERR_INVALID, "transpose: batch out of range");
+  Op op;
+  op.kind = OP_TRANSPOSE;
+  op.tr.in = static_cast<const __nv_bfloat16*>(d->in_bf16);
+  op.tr.out = static_cast<__nv_bfloat16*>(d->out_bf16);
+  op.tr.rows = d->rows; op.tr.cols = d->cols; op.tr.ld_in = d->ld_in; op.tr.ld_out = d->ld_out; op.tr.batch = d->batch;
+  op.tr.in_batch_stride = d->in_batch_stride; op.tr.out_batch_stride = d->out_batch_stride;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_attn_small_bwd(dp_engine* e, const dp_attn_small_bwd_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->T > 64) return fail(e, DP_ERR_INVALID, "attn_small_bwd: T <= 64 required");
+  Op op;
+  op.kind = OP_ATTN_SMALL_BWD;
+  op.attnb.qkv = static_cast<const __nv_bfloat16*>(d->qkv_bf16);
+  op.attnb.go = static_cast<const __nv_bfloat16*>(d->go_bf16);
+  op.attnb.out = static_cast<__nv_bfloat16*>(d->out_bf16);
+  op.attnb.B = d->B; op.attnb.T = d->T; op.attnb.heads = d->heads; op.attnb.d = d->d; op.attnb.scale = d->scale;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_grad_in(dp_engine* e, const dp_grad_in_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->C <= 0 || d->Cpad < d->C) return fail(e, DP_ERR_INVALID, "grad_in: channels");
+  Op op;
+  op.kind = OP_GRAD_IN;
+  op.gin = *d;
+  e->g_in_channels = d->C;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
 int dp_op_update(dp_engine* e, const dp_update_desc* d) {
   if (!e || !d) return DP_ERR_INVALID;
   if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
@@ -598,6 +731,10 @@ int dp_finalize(dp_engine* e, int B, int H, int W) {
   DP_CUDA(e, cudaMalloc(&e->x_init, B * hw * 3 * sizeof(float)));
   DP_CUDA(e, cudaMemset(e->x_init, 0, B * hw * 3 * sizeof(float)));
   DP_CUDA(e, cudaMalloc(&e->eps_out, B * hw * e->Cout * sizeof(float)));
+  if (e->g_in_channels > 0) {
+    DP_CUDA(e, cudaMalloc(&e->g_in, B * hw * e->g_in_channels * sizeof(float)));
+    DP_CUDA(e, cudaMemset(e->g_in, 0, B * hw * e->g_in_channels * sizeof(float)));
+  }
   DP_CUDA(e, cudaMalloc(&e->cond_per_sample, sizeof(float) * B));
   DP_CUDA(e, cudaMemset(e->cond_per_sample, 0, sizeof(float) * B));
   // eager warm-up run of both modes (sets function attributes, surfaces launch errors), then capture
@@ -645,6 +782,25 @@ int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float*
   return DP_OK;
 }
 
+int dp_unet_vjp(dp_engine* e, const float* x_nchw, const float* cond, const float* g_nchw, float* gx_nchw, void* stream) {
+  if (!e || !x_nchw || !cond || !g_nchw || !gx_nchw) return DP_ERR_INVALID;
+  if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
+  if (!e->g_in) return fail(e, DP_ERR_STATE, "the program has no data-gradient ops (no dp_op_grad_in)");
+  DP_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t s = nullptr;
+  if (int rc0 = pick_stream(e, stream, &s)) return rc0;
+  e->last_stream = s;
+  const int HW = e->H * e->W;
+  int rc = dp::launch_init_state(x_nchw, x_nchw, e->x_state, e->B, 3, HW, 1.0f, 0.0f, 0, 0, s);
+  if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
+  DP_CUDA(e, cudaMemcpyAsync(e->cond_per_sample, cond, sizeof(float) * e->B, cudaMemcpyDeviceToDevice, s));
+  DP_CUDA(e, cudaMemcpyAsync(e->g_in, g_nchw, sizeof(float) * e->B * e->g_in_channels * HW, cudaMemcpyDeviceToDevice, s));
+  DP_CUDA(e, cudaGraphLaunch(e->g_forward, s));
+  DP_CUDA(e, cudaMemcpyAsync(gx_nchw, e->eps_out, sizeof(float) * e->B * e->Cout * HW, cudaMemcpyDeviceToDevice, s));
+  if (!stream) DP_CUDA(e, cudaStreamSynchronize(s));
+  return DP_OK;
+}
+
 int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_purify_params* p, void* stream) {
   if (!e || !x0_nchw || !out_nchw || !p) return DP_ERR_INVALID;
   if (!e->finalized) return fail(e, DP_ERR_STATE, "dp_finalize has not been called");
@@ -673,6 +829,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   cp->seed = p->seed;
   cp->sample_offset = p->sample_offset;
   cp->update_kind = p->update_kind;
+  cp->states = p->states;
   DP_CUDA(e, cudaMemcpyAsync(e->d_cond, hcond, sizeof(float) * p->steps, cudaMemcpyHostToDevice, s));
   DP_CUDA(e, cudaMemcpyAsync(e->d_coef, coef8, sizeof(float) * static_cast<size_t>(p->steps) * 8, cudaMemcpyHostToDevice, s));
   DP_CUDA(e, cudaMemcpyAsync(e->d_call, cp, sizeof(*cp), cudaMemcpyHostToDevice, s));
@@ -682,6 +839,10 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
                                  p->seed, p->sample_offset, s);
   if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
+  if (p->states) {
+    rc = dp::launch_nhwc_to_nchw(e->x_state, p->states, e->B, 3, HW, s);
+    if (rc) return fail(e, DP_ERR_CUDA, "state record launch failed");
+  }
   if (p->update_kind == DP_UPDATE_LINEAR_ANCHORED) {
     if (p->anchor) {
       rc = dp::launch_init_state(p->anchor, p->anchor, e->x_init, e->B, 3, HW, 1.f, 0.f, p->seed, p->sample_offset, s);

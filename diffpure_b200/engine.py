@@ -216,6 +216,29 @@ class Engine:
             elif op.kind == "softmax_rows":
                 d = _lib.SoftmaxDesc(self._p(a["src"]), self._p(a["out"]), a["rows"], a["T"])
                 self._check(L.dp_op_softmax_rows(self.h, C.byref(d)), "dp_op_softmax_rows")
+            elif op.kind == "gn_bwd":
+                d = _lib.GnBwdDesc(self._p(a["src0"]), self._p(a["stats0"]), a["C0"], a["P0"],
+                                   1 if a["src0"].tensor.dtype == "bf16" else 0, self._p(a["src1"]),
+                                   self._p(a["stats1"]), a["C1"], a["P1"], self._p(a["gamma"]), self._p(a["beta"]),
+                                   a["B"], a["H"], a["W"], a["groups"], a["eps"], a["silu"], a["resample"],
+                                   self._p(a["g"]), self._p(a["add0"]), a["add0_scale"], self._p(a["add1"]),
+                                   self._p(a["d0_f32"]), self._p(a["d0_bf16"]), self._p(a["d1_f32"]))
+                self._check(L.dp_op_gn_bwd(self.h, C.byref(d)), "dp_op_gn_bwd")
+            elif op.kind == "softmax_bwd":
+                d = _lib.SoftmaxBwdDesc(self._p(a["pnum"]), self._p(a["rowsum"]), self._p(a["dp"]), self._p(a["ds"]),
+                                        self._p(a["pn"]), a["rows"], a["T"])
+                self._check(L.dp_op_softmax_bwd(self.h, C.byref(d)), "dp_op_softmax_bwd")
+            elif op.kind == "transpose":
+                d = _lib.TransposeDesc(self._p(a["src"]), self._p(a["out"]), a["rows"], a["cols"], a["ld_in"],
+                                       a["ld_out"], a["batch"], a["in_batch_stride"], a["out_batch_stride"])
+                self._check(L.dp_op_transpose(self.h, C.byref(d)), "dp_op_transpose")
+            elif op.kind == "attn_small_bwd":
+                d = _lib.AttnSmallBwdDesc(self._p(a["qkv"]), self._p(a["go"]), self._p(a["out"]), a["B"], a["T"],
+                                          a["heads"], a["d"], a["scale"])
+                self._check(L.dp_op_attn_small_bwd(self.h, C.byref(d)), "dp_op_attn_small_bwd")
+            elif op.kind == "grad_in":
+                d = _lib.GradInDesc(self._p(a["out"]), a["B"], a["H"], a["W"], a["C"], a["Cpad"])
+                self._check(L.dp_op_grad_in(self.h, C.byref(d)), "dp_op_grad_in")
             else:
                 raise ValueError(f"unknown op kind {op.kind}")
 
@@ -252,9 +275,22 @@ class Engine:
                     "dp_unet_forward")
         return out
 
+    def unet_vjp(self, x, cond, g_out):
+        """J(x, cond)^T g_out of one UNet evaluation (program built by a `lower_vjp`): [B,3,H,W] fp32."""
+        x = self._prep(x)
+        cond = cond.to(device=self._dev(), dtype=torch.float32).contiguous()
+        g_out = g_out.to(device=self._dev(), dtype=torch.float32).contiguous()
+        assert cond.shape == (self.B,) and g_out.shape[0] == self.B and g_out.shape[2:] == x.shape[2:]
+        out = torch.empty((self.B, 3, self.H, self.W), device=self._dev(), dtype=torch.float32)
+        self._keep = (x, cond, g_out)
+        self._check(self.lib.dp_unet_vjp(self.h, x.data_ptr(), cond.data_ptr(), g_out.data_ptr(), out.data_ptr(),
+                                         self._stream()), "dp_unet_vjp")
+        return out
+
     def purify(self, x0, cond, coef, init_scale_x, init_scale_e, *, update_kind=_lib.DP_UPDATE_LINEAR,
-               init_noise=None, step_noise=None, seed=0, sample_offset=0, anchor=None):
-        """Runs the whole loop on the device. cond: [steps] host floats; coef: [steps, ncoef] host floats."""
+               init_noise=None, step_noise=None, seed=0, sample_offset=0, anchor=None, states=None):
+        """Runs the whole loop on the device. cond: [steps] host floats; coef: [steps, ncoef] host floats.
+        states: optional [steps+1,B,3,H,W] fp32 device tensor receiving the state before every step and the final one."""
         x0 = self._prep(x0)
         cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float32))
         coef = np.ascontiguousarray(np.asarray(coef, dtype=np.float32))
@@ -269,18 +305,22 @@ class Engine:
         if anchor is not None:
             anchor = self._prep(anchor)
             assert anchor.shape == x0.shape
+        if states is not None:
+            assert states.is_cuda and states.dtype == torch.float32 and states.is_contiguous() and \
+                states.shape == (steps + 1,) + tuple(x0.shape)
         out = torch.empty_like(x0)
         p = _lib.PurifyParams(steps, update_kind, coef.shape[1], cond.ctypes.data, coef.ctypes.data,
                               float(init_scale_x), float(init_scale_e),
                               init_noise.data_ptr() if init_noise is not None else None,
                               step_noise.data_ptr() if step_noise is not None else None, int(seed),
-                              int(sample_offset), anchor.data_ptr() if anchor is not None else None)
+                              int(sample_offset), anchor.data_ptr() if anchor is not None else None,
+                              states.data_ptr() if states is not None else None)
         self._keep = (x0, init_noise, step_noise, anchor)    # inputs stay alive until the enqueued work has run
         self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), self._stream()), "dp_purify")
         return out
 
     OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "attn_small",
-                "softmax_rows", "update")
+                "softmax_rows", "update", "gn_bwd", "softmax_bwd", "transpose", "attn_small_bwd", "grad_in", "gn_finalize")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

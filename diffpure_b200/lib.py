@@ -65,11 +65,42 @@ class UpdateDesc(C.Structure):
     _fields_ = [("eps", C.c_void_p), ("ld", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int)]
 
 
+class GnBwdDesc(C.Structure):
+    _fields_ = [("src0", C.c_void_p), ("stats0", C.c_void_p), ("C0", C.c_int), ("P0", C.c_int), ("src0_is_bf16", C.c_int),
+                ("src1", C.c_void_p), ("stats1", C.c_void_p), ("C1", C.c_int), ("P1", C.c_int),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int), ("eps", C.c_float),
+                ("silu", C.c_int), ("resample", C.c_int), ("g", C.c_void_p), ("add0", C.c_void_p),
+                ("add0_scale", C.c_float), ("add1", C.c_void_p), ("d0_f32", C.c_void_p), ("d0_bf16", C.c_void_p),
+                ("d1_f32", C.c_void_p)]
+
+
+class SoftmaxBwdDesc(C.Structure):
+    _fields_ = [("pnum_bf16", C.c_void_p), ("rowsum", C.c_void_p), ("dp", C.c_void_p), ("ds_bf16", C.c_void_p),
+                ("pn_bf16", C.c_void_p), ("rows", C.c_longlong), ("T", C.c_int)]
+
+
+class TransposeDesc(C.Structure):
+    _fields_ = [("in_bf16", C.c_void_p), ("out_bf16", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int),
+                ("ld_in", C.c_int), ("ld_out", C.c_int), ("batch", C.c_int), ("in_batch_stride", C.c_longlong),
+                ("out_batch_stride", C.c_longlong)]
+
+
+class AttnSmallBwdDesc(C.Structure):
+    _fields_ = [("qkv_bf16", C.c_void_p), ("go_bf16", C.c_void_p), ("out_bf16", C.c_void_p), ("B", C.c_int),
+                ("T", C.c_int), ("heads", C.c_int), ("d", C.c_int), ("scale", C.c_float)]
+
+
+class GradInDesc(C.Structure):
+    _fields_ = [("out_bf16", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+                ("Cpad", C.c_int)]
+
+
 class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
                 ("init_noise", C.c_void_p), ("step_noise", C.c_void_p), ("seed", C.c_uint64),
-                ("sample_offset", C.c_uint64), ("anchor", C.c_void_p)]
+                ("sample_offset", C.c_uint64), ("anchor", C.c_void_p), ("states", C.c_void_p)]
 
 
 # every symbol include/diffpure_b200.h declares: name -> (restype, argtypes)
@@ -93,6 +124,12 @@ SYMBOLS = {
     "dp_op_attn_small": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallDesc)]),
     "dp_op_softmax_rows": (C.c_int, [C.c_void_p, C.POINTER(SoftmaxDesc)]),
     "dp_op_update": (C.c_int, [C.c_void_p, C.POINTER(UpdateDesc)]),
+    "dp_op_gn_bwd": (C.c_int, [C.c_void_p, C.POINTER(GnBwdDesc)]),
+    "dp_op_softmax_bwd": (C.c_int, [C.c_void_p, C.POINTER(SoftmaxBwdDesc)]),
+    "dp_op_transpose": (C.c_int, [C.c_void_p, C.POINTER(TransposeDesc)]),
+    "dp_op_attn_small_bwd": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallBwdDesc)]),
+    "dp_op_grad_in": (C.c_int, [C.c_void_p, C.POINTER(GradInDesc)]),
+    "dp_unet_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dp_program_size": (C.c_int, [C.c_void_p]),
     "dp_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "dp_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -108,10 +108,12 @@ def param_shapes(cfg):
     return shapes
 
 
-def lower(cfg, sd, B, h_bf16=True):
+def lower(cfg, sd, B, h_bf16=True, tape=None):
     """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU).
     h_bf16: store the Conv_0 output (only ever read by GroupNorm_1) in bf16 -- halves its HBM round trip; the
-    GroupNorm statistics are still accumulated from the fp32 accumulator values."""
+    GroupNorm statistics are still accumulated from the fp32 accumulator values.
+    tape: a list -> every block appends the tensors its data-gradient needs and the program stops in front of the
+    output GroupNorm / conv (`lower_vjp` appends the backward ops)."""
     S = cfg.image_size
     prog = Program(B, S, S)
     plan = module_plan(cfg)
@@ -188,6 +190,8 @@ def lower(cfg, sd, B, h_bf16=True):
             prog.gemm([act_seg(a1, cout, taps=9)], prog.const_bf16(name + ".w1", w1), cout, 9 * cout, B, Ho, Wo, cout,
                       bias=prog.const_f32(name + ".b1", P(i, "Conv_1.bias")), resid=x0.t, alpha=INV_SQRT2,
                       out_f32=out.t, stats=out.stats)
+        if tape is not None:
+            tape.append(dict(kind="res", i=i, kw=kw, x0=x0, x1=x1, h=h, out=out, shortcut=shortcut, Ho=Ho, Wo=Wo))
         return out
 
     def attnblock(i, kw, x: Act):
@@ -231,6 +235,13 @@ def lower(cfg, sd, B, h_bf16=True):
         prog.gemm([act_seg(o, C)], prog.const_bf16(name + ".w3", P(i, "NIN_3.W").t().contiguous()), C, C, B, H, W, C,
                   bias=prog.const_f32(name + ".b3", P(i, "NIN_3.b")), resid=x.t, alpha=INV_SQRT2, out_f32=out.t,
                   stats=out.stats)
+        if tape is not None:
+            rec = dict(kind="attn", i=i, x=x, out=out, T=T, C=C, scale=C ** -0.5)
+            if T <= 64:
+                rec.update(qkv=qkv)
+            else:
+                rec.update(qk=qk, vt=vt, pm=pm, rs=rs)
+            tape.append(rec)
         return out
 
     # ---- walk the module list exactly as NCSNpp.forward does (ncsnpp.py:263-381) ----------------------
@@ -269,6 +280,11 @@ def lower(cfg, sd, B, h_bf16=True):
             idx += 1
     assert not hs
     C = h.C
+    if tape is not None:
+        tape.append(dict(kind="gn_out", idx=idx, x=h))
+        tape.insert(0, dict(kind="conv_in", out=h0))
+        prog.meta.update(model="ncsnpp", out_channels=cfg.num_channels, cond="999*t")
+        return prog
     a = prog.tensor("out.a", B * S * S * C, "bf16")
     prog.gn_apply(src0=h.t, stats0=h.stats, C0=C, P0=h.P, gamma=prog.const_f32("out.gn.w", P(idx, "weight")),
                   beta=prog.const_f32("out.gn.b", P(idx, "bias")), B=B, H=S, W=S, groups=_groups(C), eps=1e-6,
@@ -279,3 +295,144 @@ def lower(cfg, sd, B, h_bf16=True):
     assert idx == len(plan)
     prog.meta.update(model="ncsnpp", out_channels=cfg.num_channels, cond="999*t")
     return prog
+
+
+def pack_dgrad3x3(w):
+    """Data gradient of a 'same' 3x3 conv = the same conv with the taps flipped and in/out swapped:
+    [Cout, Cin, 3, 3] -> [Cin, 9*Cout] with K index = (ky*3+kx)*Cout + co reading w[co, ci, 2-ky, 2-kx]."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous()
+
+
+def lower_vjp(cfg, sd, B):
+    """Forward (with a tape) followed by the data-gradient ops: the program of `dp_unet_vjp`, gx = J(x, t)^T g.
+
+    Mirrors oracle/ncsnpp_vjp.py (held to torch.autograd on the reference-identical forward): every conv / NIN contributes
+    the same tcgen05 implicit GEMM with flipped / transposed weights, GroupNorm(+SiLU, +resample, +concat) the two-pass
+    `gn_bwd` op, attention GEMMs + `softmax_bwd` + bf16 transposes (`attn_small_bwd` for T <= 64). The gradient stream is
+    fp32 (like the residual stream), GEMM operands bf16. The reference reaches this through torchsde's adjoint
+    (runners/diffpure_sde.py:233-239); here the runner differentiates the discrete Euler loop it actually runs."""
+    tape = []
+    prog = lower(cfg, sd, B, tape=tape)
+    S, nf, ncol = cfg.image_size, cfg.nf, cfg.num_channels
+
+    def P(i, name):
+        return sd[f"all_modules.{i}.{name}"].detach().float().cpu()
+
+    grad = {}        # tensor index -> (fp32 gradient, bf16 copy) of a residual-stream tensor
+    skip_grad = {}   # tensor index -> fp32 gradient that reached the tensor through its skip connection
+
+    def gpair(name, n):
+        return prog.tensor(name + ".g32", n, "f32"), prog.tensor(name + ".g16", n, "bf16")
+
+    # ---- output conv + output GroupNorm -------------------------------------------------------------------
+    rec = tape[-1]
+    hl, idx = rec["x"], rec["idx"]
+    C = hl.C
+    gin = prog.tensor("bwd.gin", B * S * S * 64, "bf16")
+    prog.grad_in(gin, B, S, S, ncol, 64)
+    wout = torch.zeros(64, C, 3, 3)
+    wout[:ncol] = P(idx + 1, "weight")
+    ga = prog.tensor("bwd.out.ga", B * S * S * C, "f32")
+    prog.gemm([act_seg(gin, 64, taps=9)], prog.const_bf16("bwd.out.w", pack_dgrad3x3(wout)), C, 9 * 64, B, S, S, C,
+              out_f32=ga)
+    g32, g16 = gpair("bwd.out", B * S * S * C)
+    prog.gn_bwd(src0=hl.t, stats0=hl.stats, C0=C, P0=hl.P, gamma=prog.const_f32("bwd.out.gn.w", P(idx, "weight")),
+                beta=prog.const_f32("bwd.out.gn.b", P(idx, "bias")), B=B, H=S, W=S, groups=_groups(C), eps=1e-6, silu=1,
+                g=ga, d0_f32=g32, d0_bf16=g16)
+    grad[hl.t.index] = (g32, g16)
+
+    def res_bwd(r):
+        i, kw, x0, x1, h, Ho, Wo = r["i"], r["kw"], r["x0"], r["x1"], r["h"], r["Ho"], r["Wo"]
+        cin, cout, mode = kw["cin"], kw["cout"], kw["mode"]
+        H, W = x0.H, x0.W
+        name = f"bwd.m{i}"
+        g32, g16 = grad.pop(r["out"].t.index)
+        ga1 = prog.tensor(name + ".ga1", B * Ho * Wo * cout, "f32")
+        prog.gemm([act_seg(g16, cout, taps=9)], prog.const_bf16(name + ".w1", pack_dgrad3x3(P(i, "Conv_1.weight"))),
+                  cout, 9 * cout, B, Ho, Wo, cout, alpha=INV_SQRT2, out_f32=ga1)
+        gc0 = prog.tensor(name + ".gc0", B * Ho * Wo * cout, "bf16")
+        prog.gn_bwd(src0=h.t, stats0=h.stats, C0=cout, P0=h.P,
+                    gamma=prog.const_f32(name + ".gn1.w", P(i, "GroupNorm_1.weight")),
+                    beta=prog.const_f32(name + ".gn1.b", P(i, "GroupNorm_1.bias")), B=B, H=Ho, W=Wo,
+                    groups=_groups(cout), eps=1e-6, silu=1, g=ga1, d0_bf16=gc0)
+        ga0 = prog.tensor(name + ".ga0", B * Ho * Wo * cin, "f32")
+        prog.gemm([act_seg(gc0, cout, taps=9)], prog.const_bf16(name + ".w0", pack_dgrad3x3(P(i, "Conv_0.weight"))),
+                  cin, 9 * cout, B, Ho, Wo, cin, out_f32=ga0)
+        if r["shortcut"]:
+            gxs = prog.tensor(name + ".gxs", B * Ho * Wo * cin, "f32")
+            prog.gemm([act_seg(g16, cout)], prog.const_bf16(name + ".w2", pack_conv1x1(P(i, "Conv_2.weight")).t().contiguous()),
+                      cin, cout, B, Ho, Wo, cin, alpha=INV_SQRT2, out_f32=gxs)
+            add0, scale = gxs, 1.0
+        else:
+            add0, scale = g32, INV_SQRT2
+        d32, d16 = gpair(name + ".dx", B * H * W * x0.C)
+        d1 = prog.tensor(name + ".dskip", B * H * W * x1.C, "f32") if x1 else None
+        prog.gn_bwd(src0=x0.t, stats0=x0.stats, C0=x0.C, P0=x0.P, src1=x1.t if x1 else None,
+                    stats1=x1.stats if x1 else None, C1=x1.C if x1 else 0, P1=x1.P if x1 else 0,
+                    gamma=prog.const_f32(name + ".gn0.w", P(i, "GroupNorm_0.weight")),
+                    beta=prog.const_f32(name + ".gn0.b", P(i, "GroupNorm_0.bias")), B=B, H=H, W=W, groups=_groups(cin),
+                    eps=1e-6, silu=1, resample=mode, g=ga0, add0=add0, add0_scale=scale,
+                    add1=skip_grad.pop(x0.t.index, None), d0_f32=d32, d0_bf16=d16, d1_f32=d1)
+        grad[x0.t.index] = (d32, d16)
+        if x1:
+            skip_grad[x1.t.index] = d1
+
+    def attn_bwd(r):
+        i, x, T, C, scale = r["i"], r["x"], r["T"], r["C"], r["scale"]
+        H, W = x.H, x.W
+        name = f"bwd.m{i}"
+        g32, g16 = grad.pop(r["out"].t.index)
+        go = prog.tensor(name + ".go", B * T * C, "bf16")
+        prog.gemm([act_seg(g16, C)], prog.const_bf16(name + ".w3", P(i, "NIN_3.W").contiguous()), C, C, 1, 1, B * T, C,
+                  alpha=INV_SQRT2, out_bf16=go)
+        dqkv = prog.tensor(name + ".dqkv", B * T * 3 * C, "bf16")
+        if T <= 64:
+            prog.attn_small_bwd(r["qkv"], go, dqkv, B, T, 1, C, scale)
+        else:
+            qk, vt, pm, rs = r["qk"], r["vt"], r["pm"], r["rs"]
+            tr = lambda nm, src, rows, cols, ld_in, ibs: _transposed(prog, name + nm, src, rows, cols, ld_in, ibs, B)  # noqa: E731
+            v = tr(".v", vt, C, T, T, C * T)                     # [B][T][C]
+            qT = tr(".qT", view(qk, 0), T, C, 2 * C, T * 2 * C)    # [B][C][T]
+            kT = tr(".kT", view(qk, C), T, C, 2 * C, T * 2 * C)
+            goT = tr(".goT", go, T, C, C, T * C)
+            dp = prog.tensor(name + ".dp", B * T * T, "f32")
+            prog.gemm([act_seg(go, C)], v, B * T, C, 1, 1, T, T, batch=B, a_batch_rows=T, b_batch_rows=T,
+                      out_batch_stride=T * T, out_f32=dp, ldc=T)
+            ds = prog.tensor(name + ".ds", B * T * T, "bf16")
+            pn = prog.tensor(name + ".pn", B * T * T, "bf16")
+            prog.softmax_bwd(pm, rs, dp, ds, pn, B * T, T)
+            dsT = tr(".dsT", ds, T, T, T, T * T)
+            pnT = tr(".pnT", pn, T, T, T, T * T)
+            bat = dict(batch=B, a_batch_rows=T, b_batch_rows=C, out_batch_stride=T * 3 * C, ldc=3 * C)
+            prog.gemm([act_seg(ds, T)], kT, B * C, T, 1, 1, T, C, alpha=scale, out_bf16=view(dqkv, 0), **bat)
+            prog.gemm([act_seg(dsT, T)], qT, B * C, T, 1, 1, T, C, alpha=scale, out_bf16=view(dqkv, C), **bat)
+            prog.gemm([act_seg(pnT, T)], goT, B * C, T, 1, 1, T, C, out_bf16=view(dqkv, 2 * C), **bat)
+        ghn = prog.tensor(name + ".ghn", B * T * C, "f32")
+        wqkv = torch.cat([P(i, f"NIN_{j}.W") for j in range(3)], dim=1).contiguous()      # [C_in, 3 C_out]
+        prog.gemm([act_seg(dqkv, 3 * C)], prog.const_bf16(name + ".wqkv", wqkv), C, 3 * C, 1, 1, B * T, C, out_f32=ghn)
+        d32, d16 = gpair(name + ".dx", B * T * C)
+        prog.gn_bwd(src0=x.t, stats0=x.stats, C0=C, P0=x.P, gamma=prog.const_f32(name + ".gn.w", P(i, "GroupNorm_0.weight")),
+                    beta=prog.const_f32(name + ".gn.b", P(i, "GroupNorm_0.bias")), B=B, H=H, W=W, groups=_groups(C),
+                    eps=1e-6, silu=0, g=ghn, add0=g32, add0_scale=INV_SQRT2, add1=skip_grad.pop(x.t.index, None),
+                    d0_f32=d32, d0_bf16=d16)
+        grad[x.t.index] = (d32, d16)
+
+    for r in reversed(tape[1:-1]):
+        (res_bwd if r["kind"] == "res" else attn_bwd)(r)
+    h0 = tape[0]["out"]
+    _, g16 = grad.pop(h0.t.index)
+    assert not grad and not skip_grad, (list(grad), list(skip_grad))
+    gx8 = prog.tensor("bwd.gx8", B * S * S * 8, "f32")
+    prog.gemm([act_seg(g16, nf, taps=9)], prog.const_bf16("bwd.conv_in.w", pack_dgrad3x3(P(2, "weight"))), ncol, 9 * nf,
+              B, S, S, 8, out_f32=gx8, ldc=8)
+    prog.update(gx8, 8, B, S, S, ncol)
+    prog.meta.update(vjp=True)
+    return prog
+
+
+def _transposed(prog, name, src, rows, cols, ld_in, in_batch_stride, B):
+    """bf16 [B][rows][cols] (row pitch ld_in) -> new tensor [B][cols][rows]."""
+    out = prog.tensor(name, B * rows * cols, "bf16")
+    prog.transpose(src, out, rows, cols, ld_in, rows, B, in_batch_stride, rows * cols)
+    return out

@@ -127,6 +127,29 @@ class Program:
                   bias=self.const_f32(name + ".b", b8), out_f32=eps, ldc=8)
         self.update(eps, 8, B, H, W, Cout)
 
+    # -- data-gradient ops (input gradient of the network; diffpure_b200/csrc/dp_bwd.cu) -------------------
+    def gn_bwd(self, *, src0, stats0, C0, P0, gamma, beta, B, H, W, groups, eps, silu, g, src1=None, stats1=None, C1=0,
+               P1=0, resample=0, add0=None, add0_scale=1.0, add1=None, d0_f32=None, d0_bf16=None, d1_f32=None):
+        self.add("gn_bwd", src0=view(src0), stats0=view(stats0), C0=C0, P0=P0, src1=view(src1), stats1=view(stats1),
+                 C1=C1, P1=P1, gamma=view(gamma), beta=view(beta), B=B, H=H, W=W, groups=groups, eps=float(eps),
+                 silu=silu, resample=resample, g=view(g), add0=view(add0), add0_scale=float(add0_scale),
+                 add1=view(add1), d0_f32=view(d0_f32), d0_bf16=view(d0_bf16), d1_f32=view(d1_f32))
+
+    def softmax_bwd(self, pnum, rowsum, dp, ds, pn, rows, T):
+        self.add("softmax_bwd", pnum=view(pnum), rowsum=view(rowsum), dp=view(dp), ds=view(ds), pn=view(pn), rows=rows,
+                 T=T)
+
+    def transpose(self, src, out, rows, cols, ld_in, ld_out, batch, in_batch_stride, out_batch_stride):
+        self.add("transpose", src=view(src), out=view(out), rows=rows, cols=cols, ld_in=ld_in, ld_out=ld_out,
+                 batch=batch, in_batch_stride=in_batch_stride, out_batch_stride=out_batch_stride)
+
+    def attn_small_bwd(self, qkv, go, out, B, T, heads, d, scale):
+        self.add("attn_small_bwd", qkv=view(qkv), go=view(go), out=view(out), B=B, T=T, heads=heads, d=d,
+                 scale=float(scale))
+
+    def grad_in(self, out, B, H, W, C, Cpad):
+        self.add("grad_in", out=view(out), B=B, H=H, W=W, C=C, Cpad=Cpad)
+
     def attn_small(self, qkv, out, B, T, heads, d, scale):
         self.add("attn_small", qkv=view(qkv), out=view(out), B=B, T=T, heads=heads, d=d, scale=float(scale))
 

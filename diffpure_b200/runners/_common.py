@@ -66,6 +66,44 @@ class VPScore(torch.nn.Module):
         raise NotImplementedError(f'Unknown score type in RevVPSDE: {self.score_type}!')
 
 
+class PurifyWithGrad(torch.autograd.Function):
+    """x0 (and the Langevin anchor) -> purified x for the linear updates
+        x_{k+1} = c0_k x_k + c1_k eps(x_k, cond_k) + c2_k z_k (+ c3_k anchor),    x_0 = sx x0 + se e,
+    differentiable in x0 and the anchor. The reference differentiates with torchsde's / torchdiffeq's continuous adjoint
+    (runners/diffpure_sde.py:233-239, diffpure_ode.py:230-238, diffpure_ldsde.py:240-243: an augmented system solved
+    backwards in time); here the backward pass is the exact gradient of the discrete loop the engine runs
+    (discretise-then-differentiate): the forward pass records the states x_k, the backward pass replays them through the
+    engine's UNet vector-Jacobian program (`dp_unet_vjp`):
+        lambda_k = c0_k lambda_{k+1} + J_k^T (c1_k lambda_{k+1}),   dL/d anchor = sum_k c3_k lambda_{k+1},   dL/dx0 = sx lambda_0.
+    Restated on the CPU by oracle/ncsnpp_vjp.py:purify_sde_vjp (held to torch.autograd through the oracle loop)."""
+
+    @staticmethod
+    def forward(ctx, x0, anchor, model, cond, coef, sx, se, e, step_noise, seed, sample_offset, update_kind):
+        dev = x0.device
+        eng = model.engine_for(x0.shape[0], dev)
+        states = torch.empty((len(cond) + 1,) + tuple(x0.shape), device=dev, dtype=torch.float32)
+        kw = dict(anchor=anchor.detach()) if anchor is not None else {}
+        out = eng.purify(x0.detach(), cond, coef, sx, se, update_kind=update_kind, init_noise=e, step_noise=step_noise,
+                         seed=seed, sample_offset=sample_offset, states=states, **kw)
+        ctx.model, ctx.cond, ctx.coef, ctx.sx, ctx.states = model, cond, np.asarray(coef, dtype=np.float32), sx, states
+        ctx.has_anchor = anchor is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        states, cond, coef = ctx.states, ctx.cond, ctx.coef
+        B, dev = states.shape[1], states.device
+        veng = ctx.model.engine_for(B, dev, vjp=True)
+        lam = g.contiguous().float()
+        ga = torch.zeros_like(lam) if ctx.has_anchor else None
+        for k in reversed(range(len(cond))):
+            if ga is not None:
+                ga = ga + float(coef[k, 3]) * lam
+            ck = torch.full((B,), float(cond[k]), device=dev)
+            lam = float(coef[k, 0]) * lam + veng.unet_vjp(states[k], ck, float(coef[k, 1]) * lam)
+        return (ctx.sx * lam, ga) + (None,) * 10
+
+
 class _Dump:
     """The reference's per-batch image dumps (only for the first two batches)."""
 
@@ -90,7 +128,7 @@ class _Dump:
 class PurifyRunner(torch.nn.Module):
     """Base of the runner classes: `self.model` is a `ScoreModel` (engine factory)."""
 
-    differentiable_error = None     # message raised for inputs that require grad (None: the runner is no_grad anyway)
+    differentiable_error = None     # message raised for inputs that require grad (None: gradients flow / no_grad runner)
     device_from_input = False       # Diffusion takes the device from the input image (runners/diffpure_ddpm.py:126,129)
 
     def _setup(self, args, config, device):
@@ -122,6 +160,17 @@ class PurifyRunner(torch.nn.Module):
         dump = _Dump(self.args, bs_id, tag)
         dump.image('original_input.png', x0)
         return x0, dev, dump
+
+    def _wants_grad(self, x):
+        """True when the caller differentiates through the loop (white-box attacks); raises for networks whose
+        input-gradient program does not exist yet instead of silently detaching."""
+        if not (torch.is_grad_enabled() and x.requires_grad):
+            return False
+        if getattr(self.model, "_lower_vjp", None) is None and not hasattr(self.model, "vjp_ok"):
+            raise NotImplementedError(
+                "diffpure_b200: backward through the purification loop is implemented for the DDPM++ (CIFAR-10) network "
+                "only; wrap the call in torch.no_grad() / detach the input for this network")
+        return True
 
     def _passes(self, x0, dump, one_pass):
         """`sample_step` purification passes, each starting from the previous one's output; returns their concatenation."""

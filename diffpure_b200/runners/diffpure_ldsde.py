@@ -8,7 +8,7 @@ import torch
 
 from .. import lib as _lib
 from .. import schedule
-from ._common import PurifyRunner, VPScore
+from ._common import PurifyRunner, PurifyWithGrad, VPScore
 from .diffpure_sde import build_score_model
 
 
@@ -42,8 +42,6 @@ class LDSDE(VPScore):
 
 
 class LDGuidedDiffusion(PurifyRunner):
-    differentiable_error = "diffpure_b200: backward through the LDSDE loop (sdeint_adjoint) is not implemented"
-
     def __init__(self, args, config, device=None, state_dict=None):
         super().__init__()
         self._setup(args, config, device)
@@ -64,9 +62,13 @@ class LDGuidedDiffusion(PurifyRunner):
         anchor = x0                                         # L216: x_init is the input image for every pass
 
         def one_pass(it, x):
-            dump.image(f'init_{it}.png', x)
+            dump.image(f'init_{it}.png', x.detach())
+            sd_ = self._call_seed(seed, it)
+            if self._wants_grad(x) or self._wants_grad(anchor):
+                return PurifyWithGrad.apply(x, anchor, self.model, cond, coef, 1.0, 0.0, torch.zeros_like(x), step_noise,
+                                            sd_, self.sample_offset, _lib.DP_UPDATE_LINEAR_ANCHORED)
             return eng.purify(x, cond, coef, 1.0, 0.0, update_kind=_lib.DP_UPDATE_LINEAR_ANCHORED,
-                              init_noise=torch.zeros_like(x), step_noise=step_noise, seed=self._call_seed(seed, it),
+                              init_noise=torch.zeros_like(x), step_noise=step_noise, seed=sd_,
                               sample_offset=self.sample_offset, anchor=anchor)
 
         return self._passes(x0, dump, one_pass)

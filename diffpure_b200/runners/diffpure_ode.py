@@ -6,8 +6,9 @@ with c2 = 0 on the same UNet programs. (The reference reads an undefined `args.f
 when absent.)"""
 import torch
 
+from .. import lib as _lib
 from .. import schedule
-from ._common import PurifyRunner, VPScore
+from ._common import PurifyRunner, PurifyWithGrad, VPScore
 from .diffpure_sde import build_score_model
 
 
@@ -31,8 +32,6 @@ class VPODE(VPScore):
 
 
 class OdeGuidedDiffusion(PurifyRunner):
-    differentiable_error = "diffpure_b200: backward through the ODE loop (odeint_adjoint) is not implemented"
-
     def __init__(self, args, config, device=None, state_dict=None):
         super().__init__()
         self._setup(args, config, device)
@@ -56,7 +55,10 @@ class OdeGuidedDiffusion(PurifyRunner):
                 e = fixed.to(dev).repeat(x.shape[0], 1, 1, 1)
             else:
                 e = torch.randn_like(x) if init_noise is None else init_noise.to(dev)
-            dump.image(f'init_{it}.png', x * sx + e * se)
+            dump.image(f'init_{it}.png', (x * sx + e * se).detach())
+            if self._wants_grad(x):      # odeint_adjoint in the reference (L230-238): here the discrete Euler loop's gradient
+                return PurifyWithGrad.apply(x, None, self.model, cond, coef, sx, se, e, None, 0, self.sample_offset,
+                                            _lib.DP_UPDATE_LINEAR)
             return eng.purify(x, cond, coef, sx, se, init_noise=e, sample_offset=self.sample_offset)
 
         return self._passes(x0, dump, one_pass)

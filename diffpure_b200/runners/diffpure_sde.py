@@ -7,14 +7,19 @@ Differences, all stated in DESIGN.md:
   * Brownian increments come from the engine's counter-based generator keyed by (seed, global sample index,
     step, pixel) -- the seed is drawn from NumPy's global RNG as torchsde's BrownianInterval does when no
     entropy is given -- or are injected (`step_noise=`) for parity tests;
-  * forward only: differentiating through the loop (torchsde adjoint) is not implemented and raises.
+  * gradients (white-box attacks, eval_sde_adv.py:126-128): the reference differentiates with torchsde's continuous
+    adjoint; here `image_editing_sample` is a torch.autograd.Function whose backward is the exact gradient of the
+    discrete Euler-Maruyama loop the engine runs (discretise-then-differentiate): the forward pass records the states
+    x_k, the backward pass replays them through the engine's UNet vector-Jacobian program (`dp_unet_vjp`),
+    lambda_k = c0_k lambda_{k+1} + J_k^T (c1_k lambda_{k+1}). Available for the DDPM++ network (CIFAR-10).
 """
 import numpy as np
 import torch
 
+from .. import lib as _lib
 from .. import schedule
 from ..model import ScoreModel
-from ._common import PurifyRunner, VPScore, _extract_into_tensor  # noqa: F401  (re-exported like the reference module)
+from ._common import PurifyRunner, PurifyWithGrad, VPScore, _extract_into_tensor  # noqa: F401  (re-exported like the reference module)
 
 
 class RevVPSDE(VPScore):
@@ -80,15 +85,14 @@ def build_score_model(config, state_dict=None):
         img_shape = (cfg.num_channels, cfg.image_size, cfg.image_size)
         if state_dict is None:
             state_dict = _load_score_sde_state('pretrained/score_sde/checkpoint_8.pth')
-        model = ScoreModel("ncsnpp", cfg, state_dict, lowering_ncsnpp.lower, out_channels=cfg.num_channels)
+        model = ScoreModel("ncsnpp", cfg, state_dict, lowering_ncsnpp.lower, out_channels=cfg.num_channels,
+                           lower_vjp_fn=lowering_ncsnpp.lower_vjp)
     else:
         raise NotImplementedError(f'Unknown dataset {config.data.dataset}!')
     return model, img_shape
 
 
 class RevGuidedDiffusion(PurifyRunner):
-    differentiable_error = ("diffpure_b200: backward through the purification loop (torchsde adjoint) is not "
-                            "implemented; wrap the call in torch.no_grad() / detach the input")
 
     def __init__(self, args, config, device=None, state_dict=None):
         """Same arguments as the reference (L151); `state_dict` optionally supplies the UNet weights
@@ -124,8 +128,13 @@ class RevGuidedDiffusion(PurifyRunner):
                 level = self.args.t + np.random.randint(-self.args.t_delta, self.args.t_delta)
                 print(f'total_noise_levels: {level}')
             sx, se = schedule.vpsde_forward_scales(level)
+            s = self._call_seed(seed, it)
+            if self._wants_grad(x):
+                dump.image(f'init_{it}.png', (x * sx + e * se).detach())
+                return PurifyWithGrad.apply(x, None, self.model, cond, coef, sx, se, e, step_noise, s,
+                                            self.sample_offset, _lib.DP_UPDATE_LINEAR)
             dump.image(f'init_{it}.png', x * sx + e * se)
-            return eng.purify(x, cond, coef, sx, se, init_noise=e, step_noise=step_noise,
-                              seed=self._call_seed(seed, it), sample_offset=self.sample_offset)       # L228-239
+            return eng.purify(x, cond, coef, sx, se, init_noise=e, step_noise=step_noise, seed=s,
+                              sample_offset=self.sample_offset)       # L228-239
 
         return self._passes(x0, dump, one_pass)

@@ -156,6 +156,50 @@ typedef struct {
   float scale;          /* applied to q.k before softmax */
 } dp_attn_small_desc;
 
+/* ---- data-gradient ops (input gradient of the score network; the reference differentiates through the loop with
+ *      torchsde's adjoint, runners/diffpure_sde.py:233-239, for the white-box attacks of eval_sde_adv.py:126-128) -------- */
+
+/* GroupNorm(+SiLU, +resample, +concat) backward of a dp_op_gn_apply: sources / statistics are the forward tensors, g is
+ * dL/d(output) in fp32 NHWC at the forward OUTPUT resolution (C0+C1 channels). Results:
+ *   d0 = dL/d(src0) + add0_scale * resample^T(add0)[:, :C0] + add1      (fp32 and / or bf16)
+ *   d1 = dL/d(src1) + add0_scale * resample^T(add0)[:, C0:]             (fp32; the skip connection's gradient) */
+typedef struct {
+  const float* src0; const float* stats0; int C0; int P0; int src0_is_bf16;
+  const float* src1; const float* stats1; int C1; int P1;
+  const float* gamma; const float* beta;
+  int B, H, W; int groups; float eps; int silu; int resample;
+  const float* g;
+  const float* add0; float add0_scale; /* optional, output resolution, C0+C1 channels (shortcut branch) */
+  const float* add1;                   /* optional, [B,H,W,C0] (gradient that reached src0 through a skip connection) */
+  float* d0_f32; void* d0_bf16; float* d1_f32;
+} dp_gn_bwd_desc;
+
+/* softmax backward per row: P = pnum / rowsum, dS = P (dP - sum_j dP_j P_j); writes dS and P as bf16. */
+typedef struct {
+  const void* pnum_bf16; const float* rowsum; const float* dp; void* ds_bf16; void* pn_bf16; long long rows; int T;
+} dp_softmax_bwd_desc;
+
+/* batched bf16 transpose: out[b][c][r] = in[b][r][c] */
+typedef struct {
+  const void* in_bf16; void* out_bf16; int rows, cols, ld_in, ld_out, batch; long long in_batch_stride, out_batch_stride;
+} dp_transpose_desc;
+
+/* backward of dp_op_attn_small: qkv as in the forward op, go = dL/d(out) [B*T, heads*d]; out = dq | dk | dv [B*T, 3*heads*d] */
+typedef struct {
+  const void* qkv_bf16; const void* go_bf16; void* out_bf16; int B, T, heads, d; float scale;
+} dp_attn_small_bwd_desc;
+
+/* dL/d(UNet output), handed to dp_unet_vjp as NCHW fp32 [B,C,H,W] -> bf16 NHWC [B,H,W,Cpad], zero padded */
+typedef struct {
+  void* out_bf16; int B, H, W, C, Cpad;
+} dp_grad_in_desc;
+
+int dp_op_gn_bwd(dp_engine* e, const dp_gn_bwd_desc* d);
+int dp_op_softmax_bwd(dp_engine* e, const dp_softmax_bwd_desc* d);
+int dp_op_transpose(dp_engine* e, const dp_transpose_desc* d);
+int dp_op_attn_small_bwd(dp_engine* e, const dp_attn_small_bwd_desc* d);
+int dp_op_grad_in(dp_engine* e, const dp_grad_in_desc* d);
+
 int dp_op_embed(dp_engine* e, const dp_embed_desc* d);
 int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d);
 int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d);
@@ -180,6 +224,11 @@ int dp_finalize(dp_engine* e, int B, int H, int W);
  * out [B,Cout,H,W] fp32 (device). Mirrors model(x, t) of the reference modules. */
 int dp_unet_forward(dp_engine* e, const float* x_nchw, const float* cond, float* out_nchw, void* stream);
 
+/* Vector-Jacobian product of one UNet evaluation for a program that contains the forward ops followed by the data-gradient
+ * ops (diffpure_b200/lowering_ncsnpp.py:lower_vjp): gx [B,3,H,W] = J(x, cond)^T g, g = dL/d(UNet output) [B,C,H,W].
+ * Same stream contract as dp_unet_forward. */
+int dp_unet_vjp(dp_engine* e, const float* x_nchw, const float* cond, const float* g_nchw, float* gx_nchw, void* stream);
+
 #define DP_UPDATE_LINEAR 0 /* x <- c[0]*x + c[1]*eps + c[2]*z                 (VP-SDE Euler-Maruyama; ddpm fixed-var) */
 #define DP_UPDATE_LEARNED_RANGE 1 /* guided_diffusion p_sample with learned-range variance and x0 clamp; 8 coefs */
 #define DP_UPDATE_LINEAR_ANCHORED 2 /* x <- c[0]*x + c[1]*eps + c[2]*z + c[3]*x_init  (Langevin-dynamics SDE, runners/diffpure_ldsde.py) */
@@ -197,6 +246,8 @@ typedef struct {
   uint64_t seed;
   uint64_t sample_offset;   /* global index of sample 0 (multi-GPU sharding keeps streams identical) */
   const float* anchor;      /* DP_UPDATE_LINEAR_ANCHORED: device [B,3,H,W] x_init, or NULL -> the (diffused) initial state */
+  float* states;            /* optional device [steps+1,B,3,H,W]: the state before every step and the final one (the
+                               discretise-then-differentiate backward pass replays the loop from them) */
 } dp_purify_params;
 
 /* The whole purification loop on the device: forward-diffuse, then `steps` x (UNet + fused update).
@@ -206,6 +257,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
  * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 attn_small,7 softmax_rows,8 update,
+ * 9 gn_bwd,10 softmax_bwd,11 transpose,12 attn_small_bwd,13 grad_in,14 gn_finalize,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

@@ -231,3 +231,93 @@ class Interp:
         p = torch.softmax(s, -1)
         o = torch.einsum("bhij,bjhd->bihd", p, v).reshape(B, T, heads * d)
         self.wr(out, o, (B, T, heads * d), (T * heads * d, heads * d, 1))
+
+    # -- data-gradient ops (dp_bwd.cu) --------------------------------------------------------------
+    def run_vjp(self, x_nchw, cond, g_nchw):
+        self.g_in = g_nchw.float()
+        return self.run(x_nchw, cond)
+
+    def op_grad_in(self, out, B, H, W, C, Cpad):
+        g = torch.zeros(B, H, W, Cpad)
+        g[..., :C] = self.g_in.permute(0, 2, 3, 1)
+        self.wr(out, g, (B, H, W, Cpad), (H * W * Cpad, W * Cpad, Cpad, 1))
+
+    @staticmethod
+    def _resample_T(t, resample):
+        """transpose of the forward resample; t: [B, Ho, Wo, C] at the forward output resolution."""
+        if resample == 1:      # forward nearest x2 -> sum of the 2x2 children
+            B, Ho, Wo, C = t.shape
+            return t.reshape(B, Ho // 2, 2, Wo // 2, 2, C).sum((2, 4))
+        if resample == 2:      # forward 2x2 mean -> a quarter of the parent
+            return t.repeat_interleave(2, 1).repeat_interleave(2, 2) * 0.25
+        return t
+
+    def op_gn_bwd(self, src0, stats0, C0, P0, src1, stats1, C1, P1, gamma, beta, B, H, W, groups, eps, silu, resample,
+                  g, add0, add0_scale, add1, d0_f32, d0_bf16, d1_f32):
+        C = C0 + C1
+        HW = H * W
+        Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
+        xs = [self.rd(src0, (B, H, W, C0))]
+        sums = [self.rd(stats0, (B, P0, C0, 2)).sum(1)]
+        if src1 is not None:
+            xs.append(self.rd(src1, (B, H, W, C1)))
+            sums.append(self.rd(stats1, (B, P1, C1, 2)).sum(1))
+        x = torch.cat(xs, -1)
+        cs = torch.cat(sums, 1).double()
+        cpg = C // groups
+        gsum = cs.reshape(B, groups, cpg, 2).sum(2)
+        n = cpg * HW
+        mean = gsum[..., 0] / n
+        var = (gsum[..., 1] / n - mean * mean).clamp_min(0)
+        rstd = (1.0 / torch.sqrt(var + eps)).float().repeat_interleave(cpg, 1)[:, None, None, :]
+        mean = mean.float().repeat_interleave(cpg, 1)[:, None, None, :]
+        xhat = (x - mean) * rstd
+        gam = self.rd(gamma, (C,))[None, None, None, :]
+        gy = self._resample_T(self.rd(g, (B, Ho, Wo, C)), resample)
+        if silu:
+            u = xhat * gam + self.rd(beta, (C,))[None, None, None, :]
+            s = torch.sigmoid(u)
+            gy = gy * (s * (1 + u * (1 - s)))
+        gx = gy * gam
+        gxg = gx.reshape(B, HW, groups, cpg)
+        xhg = xhat.reshape(B, HW, groups, cpg)
+        m1 = gxg.mean((1, 3)).repeat_interleave(cpg, 1)[:, None, None, :]
+        m2 = (gxg * xhg).mean((1, 3)).repeat_interleave(cpg, 1)[:, None, None, :]
+        d = rstd * (gx - m1 - xhat * m2)
+        if add0 is not None:
+            d = d + add0_scale * self._resample_T(self.rd(add0, (B, Ho, Wo, C)), resample)
+        d0 = d[..., :C0]
+        if add1 is not None:
+            d0 = d0 + self.rd(add1, (B, H, W, C0))
+        st0 = (HW * C0, W * C0, C0, 1)
+        if d0_f32 is not None:
+            self.wr(d0_f32, d0, (B, H, W, C0), st0)
+        if d0_bf16 is not None:
+            self.wr(d0_bf16, d0, (B, H, W, C0), st0)
+        if C1:
+            self.wr(d1_f32, d[..., C0:], (B, H, W, C1), (HW * C1, W * C1, C1, 1))
+
+    def op_softmax_bwd(self, pnum, rowsum, dp, ds, pn, rows, T):
+        P = self.rd(pnum, (rows, T)) / self.rd(rowsum, (rows,))[:, None]
+        dP = self.rd(dp, (rows, T))
+        dS = P * (dP - (dP * P).sum(-1, keepdim=True))
+        self.wr(ds, dS, (rows, T), (T, 1))
+        self.wr(pn, P, (rows, T), (T, 1))
+
+    def op_transpose(self, src, out, rows, cols, ld_in, ld_out, batch, in_batch_stride, out_batch_stride):
+        buf, off = self.flat(src)
+        x = torch.as_strided(buf, (batch, rows, cols), (in_batch_stride, ld_in, 1), off)
+        self.wr(out, x.transpose(1, 2), (batch, cols, rows), (out_batch_stride, ld_out, 1))
+
+    def op_attn_small_bwd(self, qkv, go, out, B, T, heads, d, scale):
+        x = self.rd(qkv, (B, T, 3, heads, d))
+        q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]
+        g = self.rd(go, (B, T, heads, d))
+        p = torch.softmax(torch.einsum("bihd,bjhd->bhij", q, k) * scale, -1)
+        dv = torch.einsum("bhij,bihd->bjhd", p, g)
+        dp = torch.einsum("bihd,bjhd->bhij", g, v)
+        ds = p * (dp - (dp * p).sum(-1, keepdim=True))
+        dq = torch.einsum("bhij,bjhd->bihd", ds, k) * scale
+        dk = torch.einsum("bhij,bihd->bjhd", ds, q) * scale
+        o = torch.stack([dq, dk, dv], 2).reshape(B, T, 3 * heads * d)
+        self.wr(out, o, (B, T, 3 * heads * d), (T * 3 * heads * d, 3 * heads * d, 1))

@@ -1,0 +1,107 @@
+"""GPU (-m gpu): the input gradient of the score network and of the purification loop through the C ABI
+(dp_unet_vjp + the runners' torch.autograd.Function) vs oracle/ncsnpp_vjp.py (CPU fp32, held to torch.autograd).
+
+Stated tolerance for gradients (bf16 tensor-core operands in both passes, fp32 accumulation, fp32 gradient stream):
+rel-L2 <= 3e-2 of the oracle gradient -- rounding the frozen weights to bf16 alone moves the input gradient of these
+networks by ~1.4e-2 (tests/test_vjp_lowering_cpu.py); the measured values are printed."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import ncsnpp as O, ncsnpp_vjp as V, weights
+
+pytestmark = pytest.mark.gpu
+TOL_VJP = 3e-2
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def vjp_engine(cfg, sd, B):
+    from diffpure_b200 import lowering_ncsnpp as L
+    from diffpure_b200.engine import Engine
+    lcfg = SimpleNamespace(image_size=cfg.image_size, num_channels=3, nf=cfg.nf, ch_mult=cfg.ch_mult,
+                           num_res_blocks=cfg.num_res_blocks, attn_resolutions=cfg.attn_resolutions)
+    return Engine(L.lower_vjp(lcfg, sd, B), device=0)
+
+
+@pytest.mark.parametrize("name,cfg,seed", [
+    ("tiny-small-attn", O.tiny_cfg(64, (1, 2), 1, (8,), 16), 1),
+    ("tiny-tc-attn", O.tiny_cfg(64, (1, 2, 2), 2, (16,), 32), 2),
+    ("cifar10-full", O.CIFAR10_CFG, 0),
+])
+def test_unet_vjp_vs_oracle(name, cfg, seed):
+    sd = weights.make_state_dict(O.param_shapes(cfg), seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    S, B = cfg.image_size, 2
+    x = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    t = torch.tensor([37.0, 512.0])
+    go = torch.randn(B, 3, S, S, generator=g)
+    with torch.no_grad():
+        ref = V.vjp(cfg, sd, x, t, go)
+    eng = vjp_engine(cfg, sd, B)
+    got = eng.unet_vjp(x.cuda(), t.cuda(), go.cuda()).cpu()
+    got2 = eng.unet_vjp(x.cuda(), t.cuda(), go.cuda()).cpu()
+    eng.close()
+    r = rel(got, ref)
+    print(f"unet vjp {name}: rel-L2 vs the oracle gradient = {r:.3e}")
+    assert torch.equal(got, got2)                       # deterministic: no atomics in the backward kernels either
+    assert r < TOL_VJP, r
+
+
+def _cifar_like_config(cfg):
+    return SimpleNamespace(data=SimpleNamespace(dataset="CIFAR10", image_size=cfg.image_size, num_channels=3),
+                           model=SimpleNamespace(name="ncsnpp", resblock_type="biggan", fir=False, skip_rescale=True,
+                                                 progressive="none", progressive_input="none",
+                                                 embedding_type="positional", conditional=True, nonlinearity="swish",
+                                                 nf=cfg.nf, ch_mult=list(cfg.ch_mult),
+                                                 num_res_blocks=cfg.num_res_blocks,
+                                                 attn_resolutions=list(cfg.attn_resolutions)))
+
+
+def test_runner_gradient_through_a_three_step_loop():
+    """RevGuidedDiffusion.image_editing_sample with a requires_grad input (the white-box attack path of
+    eval_sde_adv.py:126-128): d<w, purified>/dx0 over K = 3 Euler-Maruyama steps vs the oracle's discrete adjoint."""
+    from diffpure_b200.runners.diffpure_sde import RevGuidedDiffusion
+    cfg = O.tiny_cfg(64, (1, 2, 2), 1, (16,), 32)
+    sd = weights.make_state_dict(O.param_shapes(cfg), seed=2)
+    t_star = 3
+    args = SimpleNamespace(t=t_star, rand_t=False, t_delta=15, use_bm=False, score_type="score_sde", sample_step=1,
+                           log_dir="/tmp/dp_test_logs", save_images=False)
+    runner = RevGuidedDiffusion(args, _cifar_like_config(cfg), device=torch.device("cuda:0"), state_dict=sd)
+    g = torch.Generator().manual_seed(4)
+    x0 = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    e0 = torch.randn(2, 3, 32, 32, generator=g)
+    z = torch.randn(3, 2, 3, 32, 32, generator=g)
+    w = torch.randn(2, 3, 32, 32, generator=g)
+    ref, out_ref = V.purify_sde_vjp(cfg, sd, x0, t_star, e0, z, w)
+    xg = x0.cuda().requires_grad_(True)
+    out = runner.image_editing_sample(xg, bs_id=5, tag="g", init_noise=e0.cuda(), step_noise=z.cuda())
+    assert out.requires_grad
+    (gx,) = torch.autograd.grad((out * w.cuda()).sum(), xg)
+    r_out, r_g = rel(out.detach().cpu(), out_ref), rel(gx.cpu(), ref)
+    print(f"K=3 loop: state rel-L2 {r_out:.3e}, input-gradient rel-L2 {r_g:.3e}")
+    assert r_out < 5e-3 and r_g < TOL_VJP, (r_out, r_g)
+    # the no-grad path is unchanged and agrees with the differentiable one
+    with torch.no_grad():
+        out2 = runner.image_editing_sample(x0.cuda(), bs_id=5, tag="g", init_noise=e0.cuda(), step_noise=z.cuda())
+    assert torch.equal(out2, out.detach())
+    runner.model.release()
+
+
+def test_adm_gradient_request_fails_loudly():
+    """No input-gradient program exists for the ADM network yet: a requires_grad input must raise, never detach."""
+    from diffpure_b200.runners.diffpure_sde import RevGuidedDiffusion
+    from golden_inputs import ADM_TINY_REF_CONFIG
+    from oracle import adm as A
+    acfg = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    sd = weights.make_state_dict(A.param_shapes(acfg), seed=5)
+    args = SimpleNamespace(t=2, rand_t=False, t_delta=15, use_bm=False, score_type="guided_diffusion", sample_step=1,
+                           log_dir="/tmp/dp_test_logs", save_images=False)
+    config = SimpleNamespace(data=SimpleNamespace(dataset="ImageNet"), model=SimpleNamespace(**ADM_TINY_REF_CONFIG))
+    r = RevGuidedDiffusion(args, config, device=torch.device("cuda:0"), state_dict=sd)
+    with pytest.raises(NotImplementedError):
+        r.image_editing_sample(torch.zeros(2, 3, 64, 64, device="cuda").requires_grad_(True))
+    r.model.release()

@@ -29,7 +29,9 @@ class StubNet(torch.nn.Module):
         return torch.tanh(y) * (1.0 + 1e-3 * t)
 
     # Engine factory interface of diffpure_b200.model.ScoreModel
-    def engine_for(self, batch, device):
+    vjp_ok = True
+
+    def engine_for(self, batch, device, vjp=False):
         return FakeEngine(self)
 
     def release(self):
@@ -42,13 +44,15 @@ class FakeEngine:
         self.calls = []
 
     def purify(self, x0, cond, coef, init_scale_x, init_scale_e, *, update_kind=L.DP_UPDATE_LINEAR, init_noise=None,
-               step_noise=None, seed=0, sample_offset=0, anchor=None):
+               step_noise=None, seed=0, sample_offset=0, anchor=None, states=None):
         self.calls.append(dict(steps=len(cond), kind=update_kind, seed=seed, sample_offset=sample_offset))
         g = torch.Generator().manual_seed(int(seed))
         e = init_noise if init_noise is not None else torch.randn(x0.shape, generator=g)
         x = init_scale_x * x0 + init_scale_e * e
         xi = anchor if anchor is not None else x.clone()
         B = x.shape[0]
+        if states is not None:
+            states[0] = x
         coef = torch.from_numpy(np.asarray(coef, dtype=np.float32))
         for k in range(len(cond)):
             out = self.net(x, torch.full((B,), float(cond[k])))
@@ -64,7 +68,17 @@ class FakeEngine:
                 logvar = frac * c[4] + (1 - frac) * c[5]
                 x0h = (c[0] * x - c[1] * eps).clamp(-1, 1)
                 x = c[2] * x0h + c[3] * x + c[6] * torch.exp(0.5 * logvar) * z
+            if states is not None:
+                states[k + 1] = x
         return x
+
+    def unet_vjp(self, x, cond, g_out):
+        """Engine.unet_vjp contract: J(x, cond)^T g of the first three output channels' network."""
+        with torch.enable_grad():
+            xx = x.detach().clone().requires_grad_(True)
+            y = self.net(xx, cond)[:, :3]
+            (gx,) = torch.autograd.grad(y, xx, g_out)
+        return gx
 
 
 def _cifar_config():
@@ -108,8 +122,22 @@ def test_revguided_diffusion_flow_and_sde_object():
     assert torch.allclose(f, OS.rev_vpsde_f(net, "score_sde", t, x), atol=1e-5)
     assert torch.allclose(r.rev_vpsde.g(t, x.reshape(2, -1))[:, 0], OS.rev_vpsde_g(t, 2), atol=1e-6)
     assert r.rev_vpsde.noise_type == "diagonal" and r.rev_vpsde.sde_type == "ito"
-    with pytest.raises(NotImplementedError):
-        r.image_editing_sample(x.clone().requires_grad_(True))
+    # white-box gradient: the runner's discrete adjoint == autograd through the oracle loop (eval_sde_adv.py:126-128 use)
+    args.sample_step = 1
+    xg = x.clone().requires_grad_(True)
+    out = r.image_editing_sample(xg, bs_id=3, tag="t", init_noise=e, step_noise=z, seed=5)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (gx,) = torch.autograd.grad((out * w).sum(), xg)
+    xr = x.clone().requires_grad_(True)
+    (gr,) = torch.autograd.grad((OS.purify_sde(net, xr, 7, e, z) * w).sum(), xr)
+    assert torch.allclose(gx, gr, atol=1e-5, rtol=1e-4) and gx.abs().max() > 0
+    # a network without an input-gradient program must fail loudly, never detach silently
+    del StubNet.vjp_ok
+    try:
+        with pytest.raises(NotImplementedError):
+            r.image_editing_sample(x.clone().requires_grad_(True))
+    finally:
+        StubNet.vjp_ok = True
     # rand_t: the forward-diffusion level is jittered, the reverse grid is not (reference L219-231)
     args.rand_t, args.sample_step = True, 1
     np.random.seed(3)
@@ -145,6 +173,11 @@ def test_ode_and_ldsde_runners_flow():
     assert torch.allclose(out, OS.purify_ode(net, x, 12, e, step_size=1e-3), atol=2e-5)
     dx = r.vpode(torch.tensor(0.05), (x.reshape(2, -1),))[0].reshape(x.shape)
     assert torch.allclose(dx, OS.vpode_f(net, "score_sde", torch.tensor(0.05), x), atol=1e-5)
+    w = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+    xg, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)        # odeint_adjoint use (L230-238)
+    (gx,) = torch.autograd.grad((r.image_editing_sample(xg, bs_id=4, tag="o", init_noise=e) * w).sum(), xg)
+    (gr,) = torch.autograd.grad((OS.purify_ode(net, xr, 12, e, step_size=1e-3) * w).sum(), xr)
+    assert torch.allclose(gx, gr, atol=1e-5, rtol=1e-4) and gx.abs().max() > 0
 
     args = SimpleNamespace(t=30, sigma2=1e-3, lambda_ld=1e-2, eta=5, score_type="score_sde", sample_step=2,
                            log_dir="/tmp/dp_cpu_logs", save_images=False, use_bm=False)
@@ -166,6 +199,12 @@ def test_ode_and_ldsde_runners_flow():
     assert torch.allclose(out[2:], xx, atol=1e-4)
     f = r.ldsde.f(torch.tensor(0.97), p1.reshape(2, -1)).reshape(x.shape)
     assert torch.allclose(f, OS.ldsde_f(net, "score_sde", p1, x, 1e-3, 1e-2), atol=1e-4)
+    # gradient through the Langevin loop: the input is both the start state and the anchor of every step
+    args.sample_step = 1
+    xg, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((r.image_editing_sample(xg, bs_id=4, tag="l", step_noise=z) * w).sum(), xg)
+    (gr,) = torch.autograd.grad((OS.purify_ldsde(net, xr, 30, z) * w).sum(), xr)
+    assert torch.allclose(gx, gr, atol=1e-4, rtol=1e-3) and gx.abs().max() > 0
 
 
 def test_guided_and_celeba_runners_flow():
