@@ -2,8 +2,10 @@
 (dp_unet_vjp + the runners' torch.autograd.Function) vs oracle/ncsnpp_vjp.py (CPU fp32, held to torch.autograd).
 
 Stated tolerance for gradients (bf16 tensor-core operands in both passes, fp32 accumulation, fp32 gradient stream):
-rel-L2 <= 3e-2 of the oracle gradient -- rounding the frozen weights to bf16 alone moves the input gradient of these
-networks by ~1.4e-2 (tests/test_vjp_lowering_cpu.py); the measured values are printed."""
+rel-L2 <= 2e-2 of the oracle gradient, the same bound as one forward evaluation -- rounding the frozen weights to bf16
+alone moves the input gradient of the reduced networks by ~1.4e-2 (tests/test_vjp_lowering_cpu.py). Measured on B200
+(profiles/r02_vjp_parity.log): 1.57e-2 / 1.83e-2 on the reduced networks, 1.21e-2 on the full CIFAR-10 model,
+5.4e-4 for the gradient through a 3-step loop."""
 from types import SimpleNamespace
 
 import pytest
@@ -12,7 +14,7 @@ import torch
 from oracle import ncsnpp as O, ncsnpp_vjp as V, weights
 
 pytestmark = pytest.mark.gpu
-TOL_VJP = 3e-2
+TOL_VJP = 2e-2
 
 
 def rel(a, b):
