@@ -328,6 +328,13 @@ size_t dp_bytes_allocated(const dp_engine* e) { return e ? e->total_bytes : 0; }
 int dp_program_size(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
 int dp_launches_per_eval(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
 
+int dp_gemm_fused_gn_count(const dp_engine* e) {
+  int n = 0;
+  if (e)
+    for (const Op& op : e->ops) n += (op.kind == OP_GEMM && op.gemm.gn_out != nullptr) ? 1 : 0;
+  return n;
+}
+
 int dp_gemm_pair_count(const dp_engine* e) {
   int n = 0;
   if (e)
@@ -411,12 +418,58 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   const int hw = d->H * d->W;
   if (d->H > 1 && !(is_pow2(d->H) && is_pow2(d->W))) return fail(e, DP_ERR_INVALID, "gemm: H, W must be powers of two");
   if (d->H > 1 && hw < 16) return fail(e, DP_ERR_INVALID, "gemm: H*W must be >= 16");
+  // ---- fused GroupNorm output: decide whether the sample's accumulators can stay resident in TMEM ----------------
+  // HW <= 128: every tile holds whole samples (any tile kind). HW == 256: one CTA-pair tile per sample. HW == 1024: four
+  // CTA-pair tiles of BN = 128 = all 512 TMEM columns of both SMs. Anything else (or DP_GEMM_GN=0): the unfused sequence.
+  bool gn_fused = false;
+  int gn_tpg = 1, gn_stages = 2;
+  if (d->gn_out_bf16) {
+    if (d->out_f32 || d->out_bf16 || d->stats || d->resid || d->rowscale || d->silu || d->softmax || d->alpha != 1.0f ||
+        d->bias_along_m || !d->gn_gamma || !d->gn_beta || d->gn_groups <= 0 || d->N % d->gn_groups)
+      return fail(e, DP_ERR_INVALID, "gemm: the fused GroupNorm output takes bias / rowvec only and replaces every other output");
+    static const int gn_on = [] { const char* v = std::getenv("DP_GEMM_GN"); return v ? std::atoi(v) : 1; }();
+    const int cpg = d->N / d->gn_groups;
+    const bool shape_ok = (hw == 16 || hw == 64 || hw == 128 || hw == 256 || hw == 1024) && d->H > 1 && d->N % 128 == 0 &&
+                          128 % cpg == 0 && (d->batch <= 1);
+    gn_fused = gn_on && shape_ok;
+    if (!gn_fused) {
+      // unfused fallback with engine-owned scratch: raw result in bf16 + partial statistics, then finalize + apply
+      int braw, bst;
+      const size_t rows = static_cast<size_t>(d->B) * hw;
+      if (int rc = dp_buffer_alloc(e, rows * d->N * 2, &braw)) return rc;
+      const size_t srows = hw >= 128 ? rows / 128 : static_cast<size_t>((d->B + 128 / hw - 1) / (128 / hw)) * (128 / hw);
+      if (int rc = dp_buffer_alloc(e, srows * d->N * 2 * sizeof(float), &bst)) return rc;
+      dp_gemm_desc g = *d;
+      g.gn_out_bf16 = nullptr;
+      g.out_bf16 = e->buffers[braw];
+      g.stats = static_cast<float*>(e->buffers[bst]);
+      if (int rc = dp_op_gemm(e, &g)) return rc;
+      dp_gn_desc n;
+      std::memset(&n, 0, sizeof(n));
+      n.src0 = static_cast<const float*>(e->buffers[braw]);
+      n.src0_is_bf16 = 1;
+      n.stats0 = static_cast<const float*>(e->buffers[bst]);
+      n.C0 = d->N;
+      n.P0 = hw >= 128 ? hw / 128 : 1;
+      n.gamma = d->gn_gamma; n.beta = d->gn_beta;
+      n.B = d->B; n.H = d->H; n.W = d->W; n.groups = d->gn_groups; n.eps = d->gn_eps; n.silu = d->gn_silu;
+      n.out_bf16 = d->gn_out_bf16;
+      return dp_op_gn_apply(e, &n);
+    }
+    if (hw == 1024) { gn_tpg = 4; gn_stages = 4; }
+  }
   Op op;
   op.kind = OP_GEMM;
   dp::GemmParams& p = op.gemm;
   std::memset(&p, 0, sizeof(p));
   p.batch = d->batch > 0 ? d->batch : 1;
   op.softmax = d->softmax != 0;
+  if (gn_fused) {
+    p.gn_out = static_cast<__nv_bfloat16*>(d->gn_out_bf16);
+    p.gn_gamma = d->gn_gamma; p.gn_beta = d->gn_beta;
+    p.gn_cpg = d->N / d->gn_groups; p.gn_hw = hw; p.gn_eps = d->gn_eps; p.gn_silu = d->gn_silu;
+    p.tpg = gn_tpg; p.acc_stages = gn_stages;
+  }
   long long kprobe = 0;
   for (int sgi = 0; sgi < d->nseg; ++sgi) kprobe += static_cast<long long>(d->a[sgi].taps) * d->a[sgi].C;
   // tile width
@@ -426,6 +479,8 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     bn = d->N;
   } else if (d->N <= 32 && !d->stats) {
     bn = 32;  // narrow output (the C->3|6 conv padded to 8 columns): 128x32 tiles waste 4x instead of 16x of the MMA
+  } else if (gn_fused && hw == 1024) {
+    bn = 128;  // four resident accumulator stages need BN = 128
   } else if (d->N % 256 == 0 && kprobe > 512) {
     // (K <= 512: four to eight k-blocks per tile, the epilogue dominates and the 8-warp BN = 128 epilogue wins: measured
     //  80 vs 90 us and 107 vs 159 us on the 16x16 attention projections, tests/selftest_gemm perf)
@@ -490,7 +545,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   p.softmax_scale = d->softmax_scale;
   p.rowsum_out = d->rowsum_out;
   if (op.softmax && (!p.out_bf16 || !p.rowsum_out)) return fail(e, DP_ERR_INVALID, "gemm softmax needs out_bf16 + rowsum_out");
-  if (!op.softmax && !p.out_f32 && !p.out_bf16) return fail(e, DP_ERR_INVALID, "gemm: no output");
+  if (!op.softmax && !p.out_f32 && !p.out_bf16 && !p.gn_out) return fail(e, DP_ERR_INVALID, "gemm: no output");
   // CTA pairs (cta_group::2, 256 x BN tiles over two SMs) for the convolutions: less shared-memory operand traffic per
   // SM. DP_GEMM_PAIR=0 disables, 1 = BN 128 only, 2 = BN 128 and 256 (measurement switch).
   op.cg = 1;
@@ -504,8 +559,13 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     if (mode > 0 && (bn == 128 || mode > 1) && ktotal >= 1024 && units >= kMinPairTiles &&
         dp::gemm_pair_supported(p, bn, op.softmax))
       op.cg = 2;
+    if (gn_fused && hw >= 256) {  // the sample spans the pair's two CTAs: pairs are part of the algorithm, not a heuristic
+      if (!dp::gemm_pair_supported(p, bn, op.softmax)) return fail(e, DP_ERR_STATE, "gemm: fused GroupNorm needs CTA pairs");
+      op.cg = 2;
+      p.gn_xchg = 1;
+    }
   }
-  p.num_stages = dp::gemm_max_stages(bn, op.cg);
+  p.num_stages = dp::gemm_max_stages(bn, op.cg, p.gn_out != nullptr);
   if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, d->w_cols > 0 ? d->w_cols : ktotal, d->w_rows, d->w_pitch, bn / op.cg,
                         &err))
     return fail(e, DP_ERR_CUDA, "gemm: B tensor map: " + err);

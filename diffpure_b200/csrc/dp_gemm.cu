@@ -39,9 +39,13 @@ struct Smem {
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
   static constexpr int kStagingFloats = epi_warps(BN) * 32 * kStgPitch;
   static constexpr int kStatsFloats = 8 * BN * 2;
+  // fused-GroupNorm kernels only: scale/shift table [8 segments][BN][2], group statistics [8][BN/4][2],
+  // pair exchange buffers [2 parities][BN][2]
+  static constexpr int kGnFloats = 8 * BN * 2 + 8 * (BN / 4) * 2 + 2 * BN * 2;
   static constexpr int kBarBytes = 256;
-  static constexpr size_t total(int stages) {
-    return static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 + kBarBytes;
+  static constexpr size_t total(int stages, bool gn = false) {
+    return static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 + (gn ? kGnFloats * 4 : 0) +
+           kBarBytes;
   }
 };
 
@@ -50,14 +54,15 @@ struct Tile {
   int bo, hd;  // outer batch entry, head
 };
 
-// t enumerates (batch, M unit, N tile); an M unit is `cg` consecutive 128-row tiles, CTA `rank` of the pair owns one
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t, int cg = 1, int rank = 0) {
+// A work unit u enumerates (batch, M group, N tile); an M group is `tpg` consecutive M units (all of one sample when
+// tpg > 1), an M unit is `cg` consecutive 128-row tiles, CTA `rank` of the pair owns one. j = tile within the unit.
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int u, int j, int cg = 1, int rank = 0) {
   Tile c;
-  c.nt = t % p.n_tiles;
-  const int r = t / p.n_tiles;
-  const int m_units = p.m_tiles / cg;
-  c.mt = (r % m_units) * cg + rank;
-  c.b = r / m_units;
+  c.nt = u % p.n_tiles;
+  const int r = u / p.n_tiles;
+  const int m_groups = p.m_tiles / (cg * p.tpg);
+  c.mt = ((r % m_groups) * p.tpg + j) * cg + rank;
+  c.b = r / m_groups;
   c.bo = c.b / p.inner;
   c.hd = c.b - c.bo * p.inner;
   if (p.imgs_per_tile > 1) {
@@ -79,7 +84,7 @@ __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + _
 // Epilogue feature mask. The common combinations are compiled as specialisations (branch-free inner loop);
 // anything else runs the E_GENERIC instantiation, which tests the same flags at run time.
 constexpr int E_BIAS_N = 1, E_BIAS_M = 2, E_ROWVEC = 4, E_ROWSCALE = 8, E_RESID = 16, E_SILU = 32, E_F32 = 64,
-              E_BF16 = 128, E_STATS = 256, E_ALPHA = 512, E_GENERIC = 1 << 14, E_SOFTMAX = 1 << 15;
+              E_BF16 = 128, E_STATS = 256, E_ALPHA = 512, E_GN = 1 << 13, E_GENERIC = 1 << 14, E_SOFTMAX = 1 << 15;
 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -88,6 +93,7 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   static_assert(CG == 1 || (EPI & E_SOFTMAX) == 0, "the softmax epilogue is single-CTA");
   constexpr bool kSoftmax = (EPI & E_SOFTMAX) != 0;
   constexpr bool kGeneric = (EPI & E_GENERIC) != 0;
+  constexpr bool kGN = (EPI & E_GN) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* sm = smem_raw;
@@ -97,14 +103,15 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   float* staging = reinterpret_cast<float*>(sm + static_cast<size_t>(stages) * L::kStageBytes);
   float* sstats = staging + L::kStagingFloats;
   constexpr int EW = epi_warps(BN);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstats + L::kStatsFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstats + L::kStatsFloats + (kGN ? L::kGnFloats : 0));
   const uint32_t bar0 = smem_u32(bars);
-  // barrier map (8 bytes each): full[0..8) empty[8..16) tfull[16..18) tempty[18..20) ; holder at 20
+  // barrier map (8 bytes each): full[0..8) empty[8..16) tfull[16..20) tempty[20..24) xchg[24..26) ; holder at 26
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (16 + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (18 + a); };
-  volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + 20);
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (20 + a); };
+  auto xchg_bar = [&](int a) { return bar0 + 8u * (24 + a); };
+  volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,16 +126,18 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(tfull_bar(a), 1);
       // pair: one arrival per epilogue warp of either CTA, all on the leader's barrier
       mbar_init(tempty_bar(a), CG == 2 ? 2 * EW : 32 * EW);
     }
+    mbar_init(xchg_bar(0), 1);
+    mbar_init(xchg_bar(1), 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    if constexpr (CG == 2) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_holder)), 2 * BN);
-    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), 2 * BN);
+    if constexpr (CG == 2) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_holder)), p.acc_stages * BN);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), p.acc_stages * BN);
   }
   tc_fence_before_sync();
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before any remote signal
@@ -142,7 +151,10 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int work0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int work_stride = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int total_tiles = (p.m_tiles / CG) * p.n_tiles * p.batch;
+  const int tpg = p.tpg;
+  const int total_units = (p.m_tiles / (CG * tpg)) * p.n_tiles * p.batch;
+  const int ns_mask = p.acc_stages - 1;                 // accumulator stage of the it-th tile = it & ns_mask,
+  const int ns_shift = p.acc_stages == 4 ? 2 : 1;       // its barrier parity = (it >> ns_shift) & 1
   int num_kb = 0;
   for (int s = 0; s < p.nseg; ++s) num_kb += p.a[s].taps * p.a[s].kchunks;
 
@@ -151,8 +163,9 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = work0; t < total_tiles; t += work_stride) {
-        const Tile c = decode_tile(p, t, CG, rank);
+      for (int u = work0; u < total_units; u += work_stride)
+      for (int tj = 0; tj < tpg; ++tj) {
+        const Tile c = decode_tile(p, u, tj, CG, rank);
         int kglobal = 0;
         const int brow = c.nt * BN + rank * (BN / CG) + c.bo * p.b_batch_rows + c.hd * p.b_inner_rows;
         const int a_k0 = c.hd * p.a_inner_k;
@@ -194,9 +207,10 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = work0; t < total_tiles; t += work_stride, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+    for (int u = work0; u < total_units; u += work_stride)
+    for (int tj = 0; tj < tpg; ++tj, ++it) {
+      const int as = it & ns_mask;
+      const uint32_t aphase = (it >> ns_shift) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after_sync();
       const uint32_t tmem_d = tmem_base + as * BN;
@@ -250,10 +264,13 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     const float alpha = p.alpha;
     const int ldc = static_cast<int>(p.ldc);
     int it = 0;
-    for (int t = work0; t < total_tiles; t += work_stride, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const Tile c = decode_tile(p, t, CG, rank);
+    if constexpr (kGN) {
+#include "dp_gemm_gn_epilogue.inc"
+    } else
+    for (int u = work0; u < total_units; u += work_stride, ++it) {
+      const int as = it & ns_mask;
+      const uint32_t aphase = (it >> ns_shift) & 1;
+      const Tile c = decode_tile(p, u, 0, CG, rank);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       const int row0 = c.mt * kBlockM + q * 32;  // row within the batch entry
       const long long obase = static_cast<long long>(c.bo) * p.out_batch_stride +
@@ -511,28 +528,30 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
-    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
-    else tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, p.acc_stages * BN);
+    else tmem_dealloc(tmem_base, p.acc_stages * BN);
   }
 }
 
 template <int BN, int EPI>
 int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  const int total = p.m_tiles * p.n_tiles * p.batch;
+  if (p.tpg < 1 || p.m_tiles % p.tpg) return static_cast<int>(cudaErrorInvalidValue);
+  const int total = (p.m_tiles / p.tpg) * p.n_tiles * p.batch;  // work units
   if (total <= 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
-  const size_t smem = Smem<BN>::total(p.num_stages);
+  const size_t smem = Smem<BN>::total(p.num_stages, (EPI & E_GN) != 0);
   return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 1>, dim3(grid), dim3(num_threads(BN)), smem, stream, 1, p));
 }
 
 // CTA-pair launch: clusters of two CTAs, one pair per TPC
 template <int BN, int EPI>
 int launch_pair_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  const int total = (p.m_tiles / 2) * p.n_tiles * p.batch;
-  if (total <= 0 || (p.m_tiles & 1)) return static_cast<int>(cudaErrorInvalidValue);
+  if (p.tpg < 1 || (p.m_tiles % (2 * p.tpg))) return static_cast<int>(cudaErrorInvalidValue);
+  const int total = (p.m_tiles / (2 * p.tpg)) * p.n_tiles * p.batch;
+  if (total <= 0) return static_cast<int>(cudaErrorInvalidValue);
   const int pairs = total < num_sms / 2 ? total : num_sms / 2;
   return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 2>, dim3(2 * pairs), dim3(num_threads(BN)),
-                                   Smem<BN, 2>::total(p.num_stages), stream, 2, p));
+                                   Smem<BN, 2>::total(p.num_stages, (EPI & E_GN) != 0), stream, 2, p));
 }
 
 // epilogues of the convolutions, the only ops big enough for CTA pairs
@@ -606,19 +625,20 @@ int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
-size_t gemm_smem_bytes(int bn, int stages, int cg) {
-  if (cg == 2) return bn == 256 ? Smem<256, 2>::total(stages) : Smem<128, 2>::total(stages);
-  return bn == 256 ? Smem<256>::total(stages) : (bn == 32 ? Smem<32>::total(stages) : Smem<128>::total(stages));
+size_t gemm_smem_bytes(int bn, int stages, int cg, bool gn) {
+  if (cg == 2) return bn == 256 ? Smem<256, 2>::total(stages, gn) : Smem<128, 2>::total(stages, gn);
+  return bn == 256 ? Smem<256>::total(stages, gn) : (bn == 32 ? Smem<32>::total(stages, gn) : Smem<128>::total(stages, gn));
 }
 
-int gemm_max_stages(int bn, int cg) {
+int gemm_max_stages(int bn, int cg, bool gn) {
   const size_t cap = 232448;  // 227 KiB opt-in maximum per CTA on sm_100
   int s = kMaxStages;
-  while (s > 2 && gemm_smem_bytes(bn, s, cg) > cap) --s;
+  while (s > 2 && gemm_smem_bytes(bn, s, cg, gn) > cap) --s;
   return s;
 }
 
 bool gemm_pair_supported(const GemmParams& p, int bn, bool softmax) {
+  if (p.gn_out != nullptr) return !softmax && (bn == 128 || bn == 256) && (p.m_tiles % 2 == 0);
   return !softmax && (bn == 128 || bn == 256) && (p.m_tiles % 2 == 0) && pair_mask_ok(epi_mask_of(p));
 }
 
@@ -642,6 +662,19 @@ int gemm_init() {
   if (e != cudaSuccess) return static_cast<int>(e);
   DP_EPI_LIST_PAIR(X)
 #undef X
+  // fused GroupNorm epilogue
+  e = cudaFuncSetAttribute(gemm_kernel<128, E_GN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<128>::total(gemm_max_stages(128, 1, true), true)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(gemm_kernel<256, E_GN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<256>::total(gemm_max_stages(256, 1, true), true)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(gemm_kernel<128, E_GN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<128, 2>::total(gemm_max_stages(128, 2, true), true)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(gemm_kernel<256, E_GN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<256, 2>::total(gemm_max_stages(256, 2, true), true)));
+  if (e != cudaSuccess) return static_cast<int>(e);
   // narrow-N tile (output conv, N <= 32): only the plain bias epilogue and the generic fallback
   e = cudaFuncSetAttribute(gemm_kernel<32, E_BIAS_N | E_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
@@ -692,10 +725,22 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn, int c
   p.n_tiles = (N + bn - 1) / bn;
   if (p.batch <= 0) p.batch = 1;
   if (p.inner <= 0) p.inner = 1;
-  p.num_stages = gemm_max_stages(bn, cg);
+  if (p.tpg <= 0) p.tpg = 1;
+  if (p.acc_stages != 4) p.acc_stages = 2;
+  p.num_stages = gemm_max_stages(bn, cg, p.gn_out != nullptr);
 }
 
 int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream, int cg) {
+  if (p.gn_out != nullptr) {
+    // fused GroupNorm epilogue: bias / per-sample vector only, whole N tiles, groups inside a tile, accumulators of a
+    // work unit resident in TMEM
+    if (softmax || p.resid || p.rowscale || p.bias_along_m || p.silu || p.out_f32 || p.out_bf16 || p.stats ||
+        p.alpha != 1.0f || (bn != 128 && bn != 256) || p.N % bn || p.gn_cpg <= 0 || bn % p.gn_cpg || p.gn_cpg > 32 ||
+        p.tpg > p.acc_stages || p.acc_stages * bn > 512)
+      return static_cast<int>(cudaErrorInvalidValue);
+    if (cg == 2) return bn == 256 ? launch_pair_t<256, E_GN>(p, num_sms, stream) : launch_pair_t<128, E_GN>(p, num_sms, stream);
+    return bn == 256 ? launch_t<256, E_GN>(p, num_sms, stream) : launch_t<128, E_GN>(p, num_sms, stream);
+  }
   const int mask = softmax ? E_SOFTMAX : epi_mask_of(p);
   if (cg == 2) {
     if (!gemm_pair_supported(p, bn, softmax)) return static_cast<int>(cudaErrorInvalidValue);

@@ -70,6 +70,21 @@ struct GemmParams {
   // ---- softmax epilogue (kSoftmax kernels): P = exp(scale*(S - rowmax)) (bf16), rowsum out ----
   float softmax_scale;
   float* rowsum_out;  // [batch*M]
+  // ---- accumulator staging ----
+  int tpg;         // tiles per work unit: consecutive M units of ONE sample handled by the same CTA / pair (1 unless the
+                   // fused GroupNorm epilogue needs a whole 32x32 sample resident in TMEM: 4 pair tiles)
+  int acc_stages;  // TMEM accumulator stages (2; 4 = all 512 columns with BN = 128)
+  // ---- fused GroupNorm(+SiLU) output (E_GN kernels): gn_out = act(GN(acc + bias + rowvec)) as bf16, nothing else ----
+  // The statistics of a sample need every row of the sample: its tiles stay in TMEM (tpg stages), pass 1 reduces the
+  // per-channel sums (CTA pairs exchange theirs through DSMEM), pass 2 re-reads TMEM and writes the normalised operand.
+  const float* gn_gamma;
+  const float* gn_beta;
+  __nv_bfloat16* gn_out;  // same addressing as out_bf16 (ldc, batch strides)
+  int gn_cpg;             // channels per group (divides BN)
+  int gn_hw;              // rows per sample
+  float gn_eps;
+  int gn_silu;
+  int gn_xchg;            // 1: a sample spans both CTAs of the pair
 };
 
 // Launches the persistent kernel (grid = min(tiles, num_sms)). BN in {128, 256}.
@@ -78,9 +93,10 @@ struct GemmParams {
 // with BN/2-row boxes and geometry filled with the same cg.
 int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream, int cg = 1);
 bool gemm_pair_supported(const GemmParams& p, int bn, bool softmax);
-// Dynamic shared memory needed for (bn, stages); and the max stage count that fits.
-size_t gemm_smem_bytes(int bn, int stages, int cg = 1);
-int gemm_max_stages(int bn, int cg = 1);
+// Dynamic shared memory needed for (bn, stages); and the max stage count that fits. gn: the fused-GroupNorm kernels
+// (p.gn_out != nullptr) carry a scale/shift table and the pair exchange buffers.
+size_t gemm_smem_bytes(int bn, int stages, int cg = 1, bool gn = false);
+int gemm_max_stages(int bn, int cg = 1, bool gn = false);
 // One-time cudaFuncSetAttribute for all instantiations.
 int gemm_init();
 

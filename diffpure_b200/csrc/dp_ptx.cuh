@@ -183,6 +183,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote shared-memory store that signals the destination CTA's mbarrier with the bytes written (async proxy, like a TMA
+// load: a thread that observes the barrier phase complete sees the data; no fence on the sending side).
+__device__ __forceinline__ void st_async_v2_f32(uint32_t cluster_dst, float a, float b, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_dst), "f"(a), "f"(b), "r"(cluster_bar)
+               : "memory");
+}
 // TMA loads of a CTA pair: data lands in the executing CTA, completion bytes are signalled on `bar`, a
 // shared::cluster address that may live in the peer (leader) CTA.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {

@@ -193,6 +193,9 @@ class Engine:
                 d.out_f32 = self._p(a["out_f32"]); d.out_bf16 = self._p(a["out_bf16"]); d.ldc = a["ldc"]
                 d.stats = self._p(a["stats"])
                 d.softmax = a["softmax"]; d.softmax_scale = a["softmax_scale"]; d.rowsum_out = self._p(a["rowsum_out"])
+                d.gn_out_bf16 = self._p(a["gn_out"]); d.gn_gamma = self._p(a["gn_gamma"])
+                d.gn_beta = self._p(a["gn_beta"]); d.gn_groups = a["gn_groups"]; d.gn_eps = a["gn_eps"]
+                d.gn_silu = a["gn_silu"]
                 self._check(L.dp_op_gemm(self.h, C.byref(d)), "dp_op_gemm")
             elif op.kind == "gn_apply":
                 d = _lib.GnDesc(self._p(a["src0"]), self._p(a["stats0"]), a["C0"], a["P0"],
@@ -251,6 +254,11 @@ class Engine:
     def pair_gemms(self):
         """GEMM ops that run on CTA-pair (cta_group::2) tiles."""
         return self.lib.dp_gemm_pair_count(self.h)
+
+    @property
+    def fused_gn_gemms(self):
+        """GEMM ops whose epilogue applies GroupNorm(+SiLU) with the sample's accumulators resident in TMEM."""
+        return self.lib.dp_gemm_fused_gn_count(self.h)
 
     def _dev(self):
         return torch.device("cuda", self.device)

@@ -31,7 +31,9 @@ class GemmDesc(C.Structure):
                 ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int), ("rowvec_rows_per_sample", C.c_int),
                 ("rowscale", C.c_void_p), ("resid", C.c_void_p), ("alpha", C.c_float), ("silu", C.c_int),
                 ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("ldc", C.c_longlong), ("stats", C.c_void_p),
-                ("softmax", C.c_int), ("softmax_scale", C.c_float), ("rowsum_out", C.c_void_p)]
+                ("softmax", C.c_int), ("softmax_scale", C.c_float), ("rowsum_out", C.c_void_p),
+                ("gn_out_bf16", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p), ("gn_groups", C.c_int),
+                ("gn_eps", C.c_float), ("gn_silu", C.c_int)]
 
 
 class GnDesc(C.Structure):
@@ -136,6 +138,7 @@ SYMBOLS = {
     "dp_purify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PurifyParams), C.c_void_p]),
     "dp_launches_per_eval": (C.c_int, [C.c_void_p]),
     "dp_gemm_pair_count": (C.c_int, [C.c_void_p]),
+    "dp_gemm_fused_gn_count": (C.c_int, [C.c_void_p]),
     "dp_profile_ops": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                  C.POINTER(C.c_double), C.c_int]),
     "dp_normal_host": (C.c_float, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),

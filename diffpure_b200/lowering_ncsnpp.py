@@ -6,10 +6,10 @@ positional timestep embedding (layers.py:515-529), naive 2x up / 2x2-mean down (
 The state_dict uses the reference's parameter names (`all_modules.<i>.<...>`).
 
 Fusions per res-block (reference: 2 GroupNorm + 2 SiLU + 2-3 conv + Linear + adds + optional resample/cat
-= ~14 ATen ops) -> 4 kernels:
+= ~14 ATen ops) -> 3 kernels:
   gn_apply(GN0+SiLU [+up/down] [+concat] [+bf16 copy of x for the 1x1 shortcut])
-  gemm(Conv_0 3x3 + bias + Dense_0(SiLU(temb)) add + GN1 partial statistics)
-  gn_apply(GN1+SiLU)
+  gemm(Conv_0 3x3 + bias + Dense_0(SiLU(temb)) add + GroupNorm_1 + SiLU: statistics and normalisation in the epilogue,
+       the sample's accumulators resident in TMEM -> the conv result never reaches HBM)
   gemm(Conv_1 3x3 [+ Conv_2 1x1 as extra K] + biases + residual + 1/sqrt(2) + next block's GN statistics)
 All per-block Dense_0(SiLU(temb)) projections are one GEMM per step.
 """
@@ -108,10 +108,11 @@ def param_shapes(cfg):
     return shapes
 
 
-def lower(cfg, sd, B, h_bf16=True, tape=None):
+def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
     """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU).
     h_bf16: store the Conv_0 output (only ever read by GroupNorm_1) in bf16 -- halves its HBM round trip; the
     GroupNorm statistics are still accumulated from the fp32 accumulator values.
+    fuse_gn: GroupNorm_1 + act of every res-block in the epilogue of its Conv_0 GEMM (the conv result stays in TMEM).
     tape: a list -> every block appends the tensors its data-gradient needs and the program stops in front of the
     output GroupNorm / conv (`lower_vjp` appends the backward ops)."""
     S = cfg.image_size
@@ -166,18 +167,27 @@ def lower(cfg, sd, B, h_bf16=True, tape=None):
                       gamma=prog.const_f32(name + ".gn0.w", P(i, "GroupNorm_0.weight")),
                       beta=prog.const_f32(name + ".gn0.b", P(i, "GroupNorm_0.bias")),
                       B=B, H=H, W=W, groups=_groups(cin), eps=1e-6, silu=1, resample=mode, out_bf16=a0, raw_bf16=xb)
-        h = new_act(prog, name + ".h", B, cout, Ho, Wo)
-        if h_bf16:
-            h.t = prog.tensor(name + ".h16", B * Ho * Wo * cout, "bf16")
-        prog.gemm([act_seg(a0, cin, taps=9)], prog.const_bf16(name + ".w0", pack_conv3x3(P(i, "Conv_0.weight"))),
-                  cout, 9 * cin, B, Ho, Wo, cout, bias=prog.const_f32(name + ".b0", P(i, "Conv_0.bias")),
-                  rowvec=view(temb_all, dense_off[i]), rowvec_ld=n_all, rowvec_rows_per_sample=Ho * Wo,
-                  out_f32=None if h_bf16 else h.t, out_bf16=h.t if h_bf16 else None, stats=h.stats)
         a1 = prog.tensor(name + ".a1", B * Ho * Wo * cout, "bf16")
-        prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P,
-                      gamma=prog.const_f32(name + ".gn1.w", P(i, "GroupNorm_1.weight")),
-                      beta=prog.const_f32(name + ".gn1.b", P(i, "GroupNorm_1.bias")),
-                      B=B, H=Ho, W=Wo, groups=_groups(cout), eps=1e-6, silu=1, out_bf16=a1)
+        w0 = prog.const_bf16(name + ".w0", pack_conv3x3(P(i, "Conv_0.weight")))
+        b0 = prog.const_f32(name + ".b0", P(i, "Conv_0.bias"))
+        gn1w = prog.const_f32(name + ".gn1.w", P(i, "GroupNorm_1.weight"))
+        gn1b = prog.const_f32(name + ".gn1.b", P(i, "GroupNorm_1.bias"))
+        h = None
+        if fuse_gn and tape is None:
+            # Conv_0 + Dense_0(act(temb)) + GroupNorm_1 + act in ONE kernel: the conv's result is only ever read by
+            # GroupNorm_1 (layerspp.py:259-266), so it never leaves TMEM -- the epilogue writes the normalised operand
+            prog.gemm([act_seg(a0, cin, taps=9)], w0, cout, 9 * cin, B, Ho, Wo, cout, bias=b0,
+                      rowvec=view(temb_all, dense_off[i]), rowvec_ld=n_all, rowvec_rows_per_sample=Ho * Wo,
+                      gn_out=a1, gn_gamma=gn1w, gn_beta=gn1b, gn_groups=_groups(cout), gn_eps=1e-6, gn_silu=1)
+        else:
+            h = new_act(prog, name + ".h", B, cout, Ho, Wo)
+            if h_bf16:
+                h.t = prog.tensor(name + ".h16", B * Ho * Wo * cout, "bf16")
+            prog.gemm([act_seg(a0, cin, taps=9)], w0, cout, 9 * cin, B, Ho, Wo, cout, bias=b0,
+                      rowvec=view(temb_all, dense_off[i]), rowvec_ld=n_all, rowvec_rows_per_sample=Ho * Wo,
+                      out_f32=None if h_bf16 else h.t, out_bf16=h.t if h_bf16 else None, stats=h.stats)
+            prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P, gamma=gn1w, beta=gn1b,
+                          B=B, H=Ho, W=Wo, groups=_groups(cout), eps=1e-6, silu=1, out_bf16=a1)
         out = new_act(prog, name + ".out", B, cout, Ho, Wo)
         w1 = pack_conv3x3(P(i, "Conv_1.weight"))
         if shortcut:

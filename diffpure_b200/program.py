@@ -84,7 +84,10 @@ class Program:
              out_batch_stride=0, inner=1, a_inner_k=0, a_inner_rows=0, b_inner_k=0, b_inner_rows=0, out_inner_stride=0, w_cols=0,
              bias=None, bias_along_m=0, rowvec=None, rowvec_ld=0, rowvec_rows_per_sample=1,
              rowscale=None, resid=None, alpha=1.0, silu=0, out_f32=None, out_bf16=None, ldc=None, stats=None,
-             softmax=0, softmax_scale=1.0, rowsum_out=None):
+             softmax=0, softmax_scale=1.0, rowsum_out=None, gn_out=None, gn_gamma=None, gn_beta=None, gn_groups=0,
+             gn_eps=0.0, gn_silu=0):
+        """gn_out: bf16 tensor receiving act(GroupNorm(result)) -- the fused GroupNorm epilogue; the raw result is then not
+        written at all (out_f32 / out_bf16 / stats must be None)."""
         self.add("gemm", a=a, w=view(w), w_rows=w_rows, w_pitch=w_pitch, B=B, H=H, W=W, N=N, batch=batch,
                  a_batch_rows=a_batch_rows, b_batch_rows=b_batch_rows, out_batch_stride=out_batch_stride,
                  inner=inner, a_inner_k=a_inner_k, a_inner_rows=a_inner_rows, b_inner_k=b_inner_k, b_inner_rows=b_inner_rows,
@@ -92,7 +95,9 @@ class Program:
                  rowvec_rows_per_sample=rowvec_rows_per_sample, rowscale=view(rowscale), resid=view(resid),
                  alpha=float(alpha), silu=silu, out_f32=view(out_f32), out_bf16=view(out_bf16),
                  ldc=N if ldc is None else ldc, stats=view(stats), softmax=softmax,
-                 softmax_scale=float(softmax_scale), rowsum_out=view(rowsum_out))
+                 softmax_scale=float(softmax_scale), rowsum_out=view(rowsum_out), gn_out=view(gn_out),
+                 gn_gamma=view(gn_gamma), gn_beta=view(gn_beta), gn_groups=gn_groups, gn_eps=float(gn_eps),
+                 gn_silu=gn_silu)
 
     def cast(self, *, src, C, B, H, W, out_bf16, resample=0):
         """Identity gn_apply: bf16 copy (optionally resampled) of a raw fp32 stream tensor."""

@@ -106,6 +106,12 @@ typedef struct {
   float* out_f32; void* out_bf16; long long ldc;
   float* stats;          /* [ceil(M/seg)][N][2] partial (sum, sumsq), seg = min(H*W,128); or NULL */
   int softmax; float softmax_scale; float* rowsum_out;
+  /* Fused GroupNorm(+SiLU) of the result (score_sde/models/layerspp.py:259-266: Conv_0 + Dense_0(act(temb)) -> GroupNorm_1
+   * -> act, read only by Conv_1): gn_out_bf16 = act(GN(acc + bias + rowvec)) [same layout as out_bf16]. With gn_out_bf16
+   * set, out_f32 / out_bf16 / stats must be NULL (the raw result is never materialised); resid / rowscale / alpha / silu
+   * are not combined with it. Shapes the tcgen05 epilogue cannot keep resident in TMEM (a sample spanning more than 4
+   * CTA-pair tiles) fall back inside the engine to GEMM + gn_finalize + gn_apply with engine-owned scratch. */
+  void* gn_out_bf16; const float* gn_gamma; const float* gn_beta; int gn_groups; float gn_eps; int gn_silu;
 } dp_gemm_desc;
 
 typedef struct {
@@ -269,6 +275,8 @@ int dp_launches_per_eval(const dp_engine* e);
 
 /* How many of the program's GEMM ops run on CTA-pair (tcgen05 cta_group::2) tiles (tests / reporting). */
 int dp_gemm_pair_count(const dp_engine* e);
+/* How many GEMM ops carry the fused GroupNorm epilogue (requested and resident in TMEM, i.e. not fallen back). */
+int dp_gemm_fused_gn_count(const dp_engine* e);
 
 #ifdef __cplusplus
 }

@@ -94,7 +94,8 @@ class Interp:
     def op_gemm(self, a, w, w_rows, w_pitch, B, H, W, N, batch, a_batch_rows, b_batch_rows, out_batch_stride, inner,
                 a_inner_k, a_inner_rows, b_inner_k, b_inner_rows, out_inner_stride, w_cols, bias,
                 bias_along_m, rowvec, rowvec_ld, rowvec_rows_per_sample, rowscale, resid, alpha, silu, out_f32,
-                out_bf16, ldc, stats, softmax, softmax_scale, rowsum_out):
+                out_bf16, ldc, stats, softmax, softmax_scale, rowsum_out, gn_out=None, gn_gamma=None, gn_beta=None,
+                gn_groups=0, gn_eps=0.0, gn_silu=0):
         M = B * H * W
         ktot = sum(s.taps * s.C for s in a)
         for bi in range(batch):
@@ -135,6 +136,17 @@ class Interp:
                 rb, ro = self.flat(resid)
                 D = D + torch.as_strided(rb, (M, N), (ldc, 1), ro + obs)
             D = D * alpha
+            if gn_out is not None:        # fused GroupNorm(+SiLU) epilogue: statistics of the fp32 result per sample
+                assert batch == 1 and out_f32 is None and out_bf16 is None and stats is None
+                x = D.reshape(B, H * W, gn_groups, N // gn_groups)
+                mean = x.double().mean((1, 3), keepdim=True)
+                var = (x.double() * x.double()).mean((1, 3), keepdim=True) - mean * mean
+                y = ((x - mean.float()) * (1.0 / torch.sqrt(var.clamp_min(0) + gn_eps)).float()).reshape(M, N)
+                y = y * self.rd(gn_gamma, (N,))[None] + self.rd(gn_beta, (N,))[None]
+                if gn_silu:
+                    y = F.silu(y)
+                buf, off = self.flat(gn_out)
+                torch.as_strided(buf, (M, N), (ldc, 1), off + obs).copy_(_bf16(y) if self.bf else y)
             for dst in (out_f32, out_bf16):
                 if dst is not None:
                     buf, off = self.flat(dst)

@@ -1,6 +1,6 @@
 // selftest_gemm.cu -- standalone on-GPU check of the tcgen05 implicit-GEMM kernel against a plain
-// host loop (fp32 accumulation of the same bf16-rounded operands). Built by tests/build_selftest.sh,
-// run by tests/test_gpu_kernels.py (-m gpu). Exit code 0 = all cases within tolerance.
+// host loop (fp32 accumulation of the same bf16-rounded operands). Built by diffpure_b200/csrc/Makefile,
+// run by tests/test_gpu_parity.py::test_gemm_kernel_selftest (-m gpu). Exit code 0 = all cases within tolerance.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -56,6 +56,7 @@ struct ConvCase {
   bool bias, rowvec, resid, silu, stats, out_bf16;
   float alpha;
   int cg;             // 0/1 = one CTA per tile, 2 = CTA pair (cta_group::2)
+  int gn;             // 1 = fused GroupNorm + SiLU epilogue (bf16 output only; the sample's accumulators stay in TMEM)
 };
 
 static int num_sms = 148;
@@ -95,6 +96,19 @@ static void run_conv(const ConvCase& cs) {
   memset(&p, 0, sizeof(p));
   p.batch = 1;
   const int cg = cs.cg == 2 ? 2 : 1;
+  const int groups = N / 4 < 32 ? N / 4 : 32;
+  std::vector<float> gamma(N), beta(N);
+  for (auto& v : gamma) v = 1.0f + 0.3f * frand();
+  for (auto& v : beta) v = 0.3f * frand();
+  float* d_gamma = dev(gamma);
+  float* d_beta = dev(beta);
+  if (cs.gn) {
+    p.gn_out = d_outb;
+    p.gn_gamma = d_gamma; p.gn_beta = d_beta;
+    p.gn_cpg = N / groups; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
+    if (H * W == 1024) { p.tpg = 4; p.acc_stages = 4; }
+    p.gn_xchg = (cg == 2 && H * W >= 256) ? 1 : 0;
+  }
   dp::gemm_fill_geometry(p, B, H, W, N, cs.bn, cg);
   const int nsegs_total = p.m_tiles * p.stat_nseg;
   CK(cudaMalloc(&d_stats, (size_t)nsegs_total * N * 2 * 4));
@@ -138,12 +152,12 @@ static void run_conv(const ConvCase& cs) {
   p.alpha = cs.alpha;
   p.silu = cs.silu;
   // pair kernels exist for the lowerings' epilogues only: a bf16 case writes bf16 alone there
-  const bool f32_out = !((cg == 2 || !strncmp(cs.name, "bf16only", 8)) && cs.out_bf16);
+  const bool f32_out = !cs.gn && !((cg == 2 || !strncmp(cs.name, "bf16only", 8)) && cs.out_bf16);
   p.out_f32 = f32_out ? d_out : nullptr;
-  p.out_bf16 = cs.out_bf16 ? d_outb : nullptr;
+  p.out_bf16 = (cs.out_bf16 && !cs.gn) ? d_outb : nullptr;
   p.ldc = N;
   p.out_batch_stride = 0;
-  p.stats = cs.stats ? d_stats : nullptr;
+  p.stats = (cs.stats && !cs.gn) ? d_stats : nullptr;
 
   int e = dp::launch_gemm(p, cs.bn, false, num_sms, 0, cg);
   cudaError_t se = cudaDeviceSynchronize();
@@ -161,6 +175,7 @@ static void run_conv(const ConvCase& cs) {
   // host reference
   double maxerr = 0, maxref = 0, maxerr_b = 0;
   std::vector<double> rs((size_t)nsegs_total * N * 2, 0.0);
+  std::vector<float> vall(cs.gn ? (size_t)M * N : 0);
   const int hw = H * W;
   const int seg_rows = hw >= 128 ? 128 : hw;
   for (int b = 0; b < B; ++b)
@@ -190,6 +205,7 @@ static void run_conv(const ConvCase& cs) {
           if (cs.silu) v = v / (1.f + expf(-v));
           if (cs.resid) v += resid[row * N + n];
           v *= cs.alpha;
+          if (cs.gn) { vall[row * N + n] = v; continue; }
           const double d = f32_out ? fabs((double)v - out[row * N + n]) : 0.0;
           if (d > maxerr) maxerr = d;
           if (fabs(v) > maxref) maxref = fabs(v);
@@ -202,21 +218,44 @@ static void run_conv(const ConvCase& cs) {
           rs[(sg * N + n) * 2 + 1] += (double)v * v;
         }
       }
+  if (cs.gn) {  // per (sample, group) statistics in double, then normalise + affine + SiLU; compare with the bf16 output
+    const int cpg = N / groups;
+    for (int b = 0; b < B; ++b)
+      for (int g = 0; g < groups; ++g) {
+        double S = 0, Q = 0;
+        for (int px = 0; px < hw; ++px)
+          for (int j = 0; j < cpg; ++j) {
+            const double v = vall[((size_t)b * hw + px) * N + g * cpg + j];
+            S += v;
+            Q += v * v;
+          }
+        const double n = (double)cpg * hw, mean = S / n, rstd = 1.0 / sqrt(fmax(Q / n - mean * mean, 0.0) + 1e-6);
+        for (int px = 0; px < hw; ++px)
+          for (int j = 0; j < cpg; ++j) {
+            const int n_ = g * cpg + j;
+            const size_t i = ((size_t)b * hw + px) * N + n_;
+            double y = (vall[i] - mean) * rstd * gamma[n_] + beta[n_];
+            y = y / (1.0 + exp(-y));
+            maxerr_b = fmax(maxerr_b, fabs(y - __bfloat162float(outb[i])));
+            maxref = fmax(maxref, fabs(y));
+          }
+      }
+  }
   double maxs = 0, maxsref = 0;
-  if (cs.stats) {
+  if (cs.stats && !cs.gn) {
     const size_t nvalid = (size_t)((M + seg_rows - 1) / seg_rows) * N * 2;
     for (size_t i = 0; i < nvalid; ++i) {
       maxs = fmax(maxs, fabs(rs[i] - stats[i]));
       maxsref = fmax(maxsref, fabs(rs[i]));
     }
   }
-  const bool ok = maxerr <= 2e-3 * fmax(1.0, maxref) && (!cs.out_bf16 || maxerr_b <= 1e-2 * fmax(1.0, maxref)) &&
-                  (!cs.stats || maxs <= 1e-3 * fmax(1.0, maxsref));
+  const bool ok = maxerr <= 2e-3 * fmax(1.0, maxref) && (!(cs.out_bf16 || cs.gn) || maxerr_b <= 1e-2 * fmax(1.0, maxref)) &&
+                  (!cs.stats || cs.gn || maxs <= 1e-3 * fmax(1.0, maxsref));
   printf("[%s] %s  max|err|=%.3e (max|ref|=%.3f) bf16out err=%.3e stats err=%.3e (ref %.2f)\n", cs.name,
          ok ? "OK  " : "FAIL", maxerr, maxref, maxerr_b, maxs, maxsref);
   if (!ok) failures++;
   cudaFree(d_a0); cudaFree(d_a1); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_rowvec); cudaFree(d_resid);
-  cudaFree(d_out); cudaFree(d_outb); cudaFree(d_stats);
+  cudaFree(d_out); cudaFree(d_outb); cudaFree(d_stats); cudaFree(d_gamma); cudaFree(d_beta);
 }
 
 // Batched attention-style GEMMs: S = softmax-numerator(Q K^T) then O = P V^T-layout.
@@ -323,6 +362,14 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
   if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, bn / cg, &err)) { printf("%s\n", err.c_str()); exit(1); }
   p.bias = d_bias; p.alpha = 1.f; p.out_f32 = d_out; p.ldc = N; p.stats = d_stats;
   if (getenv("DP_PERF_BF16")) { p.out_f32 = nullptr; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d_out); }  // bf16 output epilogue
+  if (getenv("DP_PERF_GN")) {  // fused GroupNorm + SiLU epilogue (bf16 output only)
+    p.out_f32 = nullptr; p.out_bf16 = nullptr; p.stats = nullptr;
+    p.gn_out = reinterpret_cast<__nv_bfloat16*>(d_out);
+    p.gn_gamma = d_bias; p.gn_beta = d_bias; p.gn_cpg = N / 32; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
+    if (H * W == 1024) { p.tpg = 4; p.acc_stages = 4; }
+    p.gn_xchg = (cg == 2 && H * W >= 256) ? 1 : 0;
+    dp::gemm_fill_geometry(p, B, H, W, N, bn, cg);
+  }
   int sh = 0; while ((1 << sh) < H * W) ++sh;
   if (resid) { p.resid = d_res; p.alpha = 0.70710678f; } else { p.rowvec = d_rowvec; p.rowvec_ld = N; p.rowvec_shift = sh; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -387,6 +434,16 @@ int main(int argc, char** argv) {
       {"pair conv3x3 4x4 256->256",    32, 4, 4,  256, 9,  0, 256, 256, 1, true, false,true, false,true, false, 0.70710678f, 2},
       {"pair conv3x3 s2 32->16 128",   2, 16, 16, 128, 9,  0, 128, 128, 2, true, false,false,false,true, false, 1.f, 2},
       {"pair conv 64x64 many tiles",   20, 64, 64, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f, 2},
+      // fused GroupNorm + SiLU epilogue: the sample's accumulators resident in TMEM, two passes
+      {"gn pair 32x32 128->128 (4 resident tiles, pair exchange)", 3, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn pair 32x32 256->256 (two N tiles)",                    2, 32, 32, 256, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn pair 32x32 many samples",                              40, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn pair 16x16 256->256 bn256 (pair exchange)",            5, 16, 16, 256, 9, 0, 256, 256, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn pair 16x16 512->256 bn128 many",                       90, 16, 16, 512, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn single 8x8 256 bn128 (ragged)",                        5, 8,  8,  256, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 1, 1},
+      {"gn pair 8x8 256 bn128",                                   8, 8,  8,  256, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn single 4x4 256 bn256 (ragged)",                        11, 4, 4,  256, 9, 0, 256, 256, 1, true, true, false,false,false,true, 1.f, 1, 1},
+      {"gn pair 4x4 256 bn128 no rowvec",                         32, 4, 4,  256, 9, 0, 256, 128, 1, true, false,false,false,false,true, 1.f, 2, 1},
   };
   const int ncases = sizeof(cases) / sizeof(cases[0]);
   for (int i = 0; i < ncases; ++i) {
