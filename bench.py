@@ -382,7 +382,7 @@ def measure(name, B, steps, warmup, rank, world, local, dev, dist, want_e2e=True
                "api": f"{R.__module__}.{R.__name__}.image_editing_sample"}
 
     res = {"value": value, "ms_per_step": ms_total / steps, "clocks": clocks, "e2e": e2e, "nsteps": nsteps,
-           "launches": steps * (nsteps * (eng.launches_per_eval + 1) + 2), "B": B}
+           "launches": steps * (nsteps * eng.launches_per_step + 2), "B": B}
     if rank == 0:
         res["roofline"] = roofline_of(eng, wl, B, value / world, nsteps)
     res["engine"] = eng

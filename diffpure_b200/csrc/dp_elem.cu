@@ -6,6 +6,7 @@
 
 #include "dp_elem.cuh"
 #include "dp_launch.cuh"
+#include "dp_rng.cuh"
 
 #include <cstdio>
 
@@ -28,36 +29,9 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& a, float& b) {
 
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------
-// Counter-based normals (Philox4x32-10 + Box-Muller)
-// ------------------------------------------------------------------------------------------------
-__host__ __device__ static inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
-                                                    uint32_t k0, uint32_t k1) {
-  const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
-  const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
-  const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
-  const uint32_t n1 = static_cast<uint32_t>(p1);
-  const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
-  const uint32_t n3 = static_cast<uint32_t>(p0);
-  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-}
-
 __host__ __device__ float dp_normal(unsigned long long seed, unsigned long long sample, unsigned int stream,
                                     unsigned int pixel, int c) {
-  uint32_t c0 = static_cast<uint32_t>(sample), c1 = static_cast<uint32_t>(sample >> 32), c2 = stream, c3 = pixel;
-  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c0, c1, c2, c3, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  const uint32_t a = (c < 2) ? c0 : c2, b = (c < 2) ? c1 : c3;
-  const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float rad = sqrtf(-2.0f * logf(u1));
-  const float ang = 6.283185307179586f * u2;
-  return (c == 1) ? rad * sinf(ang) : rad * cosf(ang);
+  return dp_normal_impl(seed, sample, stream, pixel, c);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -42,6 +42,7 @@ struct Op {
   int bn = 128;
   int cg = 1;  // CTAs per tile
   bool softmax = false;
+  int fused_update_op = -1;  // GEMM: index of the OP_UPDATE its epilogue absorbs in step mode; OP_UPDATE: index of that GEMM
   dp::GnParams gn;
   dp_stats_desc stats;
   StatsReduce sred;
@@ -68,6 +69,7 @@ struct dp_engine {
   size_t total_bytes = 0;
   std::vector<Op> ops;
   bool finalized = false;
+  bool update_fused = false;  // the per-step update (and the step-counter advance) run inside the output conv's epilogue
   int B = 0, H = 0, W = 0, Cout = 0;
   // engine-owned run state
   float* x_state = nullptr;          // NHWC fp32 [B,H,W,3]
@@ -152,6 +154,18 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       break;
     }
     case OP_GEMM:
+      if (mode != 0 && op.fused_update_op >= 0) {
+        // step mode: the output conv applies the update in its epilogue (no eps tensor, no update / step-advance launch)
+        const dp::UpdateParams& u = e->ops[op.fused_update_op].upd;
+        dp::GemmParams g = op.gemm;
+        g.out_f32 = nullptr;
+        g.upd_x = e->x_state; g.upd_x_init = e->x_init;
+        g.upd_step = e->d_step; g.upd_step_rw = e->d_step; g.upd_coef = e->d_coef; g.upd_call = e->d_call;
+        g.upd_arrive = mode == 1 ? e->d_step + 1 : nullptr;   // mode 2 (profiling): the step counter stays put
+        g.upd_cout = u.Cout; g.upd_hw = u.H * u.W; g.upd_B = u.B;
+        rc = dp::launch_gemm(g, op.bn, op.softmax, e->num_sms, s, op.cg);
+        break;
+      }
       rc = dp::launch_gemm(op.gemm, op.bn, op.softmax, e->num_sms, s, op.cg);
       break;
     case OP_GN:
@@ -176,6 +190,7 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       rc = dp::launch_attn_small(op.attn, s);
       break;
     case OP_UPDATE: {
+      if (mode != 0 && op.fused_update_op >= 0) break;  // absorbed by the output conv's epilogue
       dp::UpdateParams u = op.upd;
       u.mode = mode;
       u.out_nchw = e->eps_out;
@@ -221,7 +236,7 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
 int run_ops(dp_engine* e, int mode, cudaStream_t s) {
   for (size_t i = 0; i < e->ops.size(); ++i)
     if (int rc = run_op(e, i, mode, s)) return rc;
-  if (mode == 1) {
+  if (mode == 1 && !e->update_fused) {
     int rc = dp::launch_step_advance(e->d_step, s);
     if (rc) return fail(e, DP_ERR_CUDA, "launch_step_advance failed");
   }
@@ -327,6 +342,11 @@ int dp_device_sm_count(const dp_engine* e) { return e ? e->num_sms : 0; }
 size_t dp_bytes_allocated(const dp_engine* e) { return e ? e->total_bytes : 0; }
 int dp_program_size(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
 int dp_launches_per_eval(const dp_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
+int dp_launches_per_step(const dp_engine* e) {
+  // one replay of the step graph: with the update in the output conv's epilogue there is neither an update nor a
+  // step-advance launch; otherwise both
+  return e ? static_cast<int>(e->ops.size()) + (e->update_fused ? -1 : 1) : 0;
+}
 
 int dp_gemm_fused_gn_count(const dp_engine* e) {
   int n = 0;
@@ -775,6 +795,19 @@ int dp_op_update(dp_engine* e, const dp_update_desc* d) {
   op.upd.eps = d->eps; op.upd.ld = d->ld; op.upd.B = d->B; op.upd.H = d->H; op.upd.W = d->W; op.upd.Cout = d->Cout;
   op.upd.tables = tables_of(e, 8);
   e->Cout = d->Cout;
+  // The producer of `eps` is the C -> 3|6 output conv on the narrow tile: in step mode its epilogue applies the update
+  // (DP_FUSE_UPDATE=0 keeps the separate kernel, for A/B runs).
+  static const int fuse = [] { const char* v = std::getenv("DP_FUSE_UPDATE"); return v ? std::atoi(v) : 1; }();
+  if (fuse && !e->ops.empty()) {
+    Op& g = e->ops.back();
+    if (g.kind == OP_GEMM && g.bn == 32 && g.cg == 1 && !g.softmax && g.gemm.out_f32 == d->eps && !g.gemm.out_bf16 &&
+        !g.gemm.resid && !g.gemm.rowvec && !g.gemm.rowscale && !g.gemm.stats && !g.gemm.silu && g.gemm.alpha == 1.0f &&
+        !g.gemm.bias_along_m && g.gemm.batch == 1 && g.gemm.ldc == d->ld && g.gemm.M == d->B * d->H * d->W) {
+      g.fused_update_op = static_cast<int>(e->ops.size());
+      op.fused_update_op = static_cast<int>(e->ops.size()) - 1;
+      e->update_fused = true;
+    }
+  }
   e->ops.push_back(op);
   return DP_OK;
 }
@@ -894,7 +927,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   DP_CUDA(e, cudaMemcpyAsync(e->d_coef, coef8, sizeof(float) * static_cast<size_t>(p->steps) * 8, cudaMemcpyHostToDevice, s));
   DP_CUDA(e, cudaMemcpyAsync(e->d_call, cp, sizeof(*cp), cudaMemcpyHostToDevice, s));
   DP_CUDA(e, cudaEventRecord(e->staging_done, s));
-  DP_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int), s));
+  DP_CUDA(e, cudaMemsetAsync(e->d_step, 0, 2 * sizeof(int), s));  // step counter + the CTA arrival counter beside it
   const int HW = e->H * e->W;
   int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
                                  p->seed, p->sample_offset, s);
@@ -929,7 +962,7 @@ int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops,
   int rc = DP_OK;
   for (int i = 0; i < n && rc == DP_OK; ++i) {
     cudaEventRecord(ev[2 * i], e->stream);
-    rc = run_op(e, i, mode, e->stream);
+    rc = run_op(e, i, mode == 1 ? 2 : mode, e->stream);  // 2 = step mode without advancing the step counter
     cudaEventRecord(ev[2 * i + 1], e->stream);
   }
   if (rc == DP_OK) {

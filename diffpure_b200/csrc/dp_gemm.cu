@@ -13,8 +13,10 @@
 // CG = 2 runs the same roles on a CTA pair (cluster of 2, tcgen05 cta_group::2): a 256 x BN tile, each CTA staging its own
 // 128 rows of A and half of B, the leader CTA's warp 1 issuing the MMAs for both SMs (see Smem<> and the CG == 2 branches).
 #include "dp_gemm.cuh"
+#include "dp_elem.cuh"
 #include "dp_launch.cuh"
 #include "dp_ptx.cuh"
+#include "dp_rng.cuh"
 
 #include <cstdio>
 
@@ -84,7 +86,8 @@ __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + _
 // Epilogue feature mask. The common combinations are compiled as specialisations (branch-free inner loop);
 // anything else runs the E_GENERIC instantiation, which tests the same flags at run time.
 constexpr int E_BIAS_N = 1, E_BIAS_M = 2, E_ROWVEC = 4, E_ROWSCALE = 8, E_RESID = 16, E_SILU = 32, E_F32 = 64,
-              E_BF16 = 128, E_STATS = 256, E_ALPHA = 512, E_GN = 1 << 13, E_GENERIC = 1 << 14, E_SOFTMAX = 1 << 15;
+              E_BF16 = 128, E_STATS = 256, E_ALPHA = 512, E_UPDATE = 1 << 12, E_GN = 1 << 13, E_GENERIC = 1 << 14,
+              E_SOFTMAX = 1 << 15;
 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -94,6 +97,8 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   constexpr bool kSoftmax = (EPI & E_SOFTMAX) != 0;
   constexpr bool kGeneric = (EPI & E_GENERIC) != 0;
   constexpr bool kGN = (EPI & E_GN) != 0;
+  constexpr bool kUpdate = (EPI & E_UPDATE) != 0;
+  static_assert(!kUpdate || (BN == 32 && CG == 1), "the fused update epilogue belongs to the narrow output-conv tile");
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* sm = smem_raw;
@@ -266,6 +271,65 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
     int it = 0;
     if constexpr (kGN) {
 #include "dp_gemm_gn_epilogue.inc"
+    } else if constexpr (kUpdate) {
+      // ---- the per-step update as the output conv's epilogue (north_star: "fused into the UNet epilogue so no extra
+      // elementwise kernel launches per step"): one lane = one TMEM lane = one pixel, eps = acc[0..Cout) + bias straight
+      // from TMEM, then x <- update(x, eps, z) in place (runners/diffpure_sde.py:86-147 + torchsde Euler;
+      // gaussian_diffusion.py:277-284,305,317-322,438-446; diffpure_ddpm.py:37-54; diffpure_ode.py:90-131; diffpure_ldsde.py:92-148)
+      const int step = *p.upd_step;
+      const CallParams cp = *static_cast<const CallParams*>(p.upd_call);
+      float k[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k[i] = p.upd_coef[step * 8 + i];
+      float bia[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) bia[j] = (p.bias != nullptr && j < p.upd_cout) ? p.bias[j] : 0.f;
+      const int HW = p.upd_hw;
+      for (int u = work0; u < total_units; u += work_stride, ++it) {
+        const int as = it & ns_mask;
+        const uint32_t aphase = (it >> ns_shift) & 1;
+        const Tile c = decode_tile(p, u, 0, CG, rank);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+        uint32_t r[32];
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after_sync();
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(tempty_bar(as));
+        const long long gp = static_cast<long long>(c.mt) * kBlockM + q * 32 + lane;  // global pixel = output row
+        if (gp < p.M) {
+          const int b = static_cast<int>(gp / HW);
+          const int pix = static_cast<int>(gp - static_cast<long long>(b) * HW);
+          float o[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) o[j] = __uint_as_float(r[j]) + bia[j];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float* xp = p.upd_x + gp * 3 + ch;
+            const float xv = *xp;
+            const float z = cp.step_noise
+                                ? cp.step_noise[((static_cast<size_t>(step) * p.upd_B + b) * 3 + ch) * HW + pix]
+                                : dp_normal_impl(cp.seed, cp.sample_offset + b, static_cast<unsigned>(step) + 1u,
+                                                 static_cast<unsigned>(pix), ch);
+            float xn;
+            if (cp.update_kind == 0) {
+              xn = k[0] * xv + k[1] * o[ch] + k[2] * z;
+            } else if (cp.update_kind == 2) {
+              xn = k[0] * xv + k[1] * o[ch] + k[2] * z + k[3] * p.upd_x_init[gp * 3 + ch];
+            } else {
+              float x0 = k[0] * xv - k[1] * o[ch];
+              x0 = fminf(1.f, fmaxf(-1.f, x0));
+              const float mean = k[2] * x0 + k[3] * xv;
+              const float frac = (o[3 + ch] + 1.f) * 0.5f;
+              const float logvar = frac * k[4] + (1.f - frac) * k[5];
+              xn = mean + k[6] * expf(0.5f * logvar) * z;
+            }
+            *xp = xn;
+            if (cp.states) cp.states[((static_cast<size_t>(step + 1) * p.upd_B + b) * 3 + ch) * HW + pix] = xn;
+          }
+        }
+      }
     } else
     for (int u = work0; u < total_units; u += work_stride, ++it) {
       const int as = it & ns_mask;
@@ -526,6 +590,16 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   tc_fence_before_sync();
   if constexpr (CG == 2) cluster_sync_all();  // no CTA of the pair may exit while its peer can still signal it
   else __syncthreads();
+  if constexpr (kUpdate) {
+    // every thread of this CTA has read the step counter; the last CTA to get here advances it for the next replay
+    if (threadIdx.x == 0 && p.upd_arrive != nullptr) {
+      __threadfence();
+      if (atomicAdd(p.upd_arrive, 1) == static_cast<int>(gridDim.x) - 1) {
+        *p.upd_arrive = 0;
+        *p.upd_step_rw = *p.upd_step_rw + 1;
+      }
+    }
+  }
   if (warp == 2) {
     tc_fence_after_sync();
     if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, p.acc_stages * BN);
@@ -682,6 +756,9 @@ int gemm_init() {
   e = cudaFuncSetAttribute(gemm_kernel<32, E_GENERIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(gemm_kernel<32, E_UPDATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(Smem<32>::total(gemm_max_stages(32))));
+  if (e != cudaSuccess) return static_cast<int>(e);
   return 0;
 }
 
@@ -747,6 +824,10 @@ int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStre
     return bn == 256 ? dispatch_pair<256>(p, mask, num_sms, stream) : dispatch_pair<128>(p, mask, num_sms, stream);
   }
   if (bn == 32) {
+    if (p.upd_x != nullptr) {
+      if (cg != 1 || softmax || p.upd_cout > 6 || p.N > 32) return static_cast<int>(cudaErrorInvalidValue);
+      return launch_t<32, E_UPDATE>(p, num_sms, stream);
+    }
     if (mask == (E_BIAS_N | E_F32)) return launch_t<32, E_BIAS_N | E_F32>(p, num_sms, stream);
     return launch_t<32, E_GENERIC>(p, num_sms, stream);
   }

@@ -85,6 +85,16 @@ struct GemmParams {
   float gn_eps;
   int gn_silu;
   int gn_xchg;            // 1: a sample spans both CTAs of the pair
+  // ---- fused per-step update (E_UPDATE kernel: the C -> 3|6 output conv, BN = 32): the epilogue applies the SDE / DDPM
+  // update to the state instead of writing eps, draws the noise, and the last CTA advances the step counter ----
+  float* upd_x;             // state, NHWC fp32 [B*H*W, 3]; null = plain epilogue
+  const float* upd_x_init;  // anchor of the Langevin-dynamics update
+  const int* upd_step;      // device step counter
+  const float* upd_coef;    // [steps][8]
+  const void* upd_call;     // dp::CallParams*: noise source, seed, sample offset, update kind, state recording
+  int* upd_arrive;          // CTA arrival counter next to the step counter (null: do not advance, profiling)
+  int* upd_step_rw;
+  int upd_cout, upd_hw, upd_B;
 };
 
 // Launches the persistent kernel (grid = min(tiles, num_sms)). BN in {128, 256}.

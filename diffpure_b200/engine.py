@@ -251,6 +251,11 @@ class Engine:
         return self.lib.dp_launches_per_eval(self.h)
 
     @property
+    def launches_per_step(self):
+        """Kernels per loop step (the update is the output conv's epilogue: no extra launch)."""
+        return self.lib.dp_launches_per_step(self.h)
+
+    @property
     def pair_gemms(self):
         """GEMM ops that run on CTA-pair (cta_group::2) tiles."""
         return self.lib.dp_gemm_pair_count(self.h)

@@ -137,6 +137,7 @@ SYMBOLS = {
     "dp_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dp_purify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PurifyParams), C.c_void_p]),
     "dp_launches_per_eval": (C.c_int, [C.c_void_p]),
+    "dp_launches_per_step": (C.c_int, [C.c_void_p]),
     "dp_gemm_pair_count": (C.c_int, [C.c_void_p]),
     "dp_gemm_fused_gn_count": (C.c_int, [C.c_void_p]),
     "dp_profile_ops": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int),

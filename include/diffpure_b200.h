@@ -270,8 +270,11 @@ int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops,
 /* Host evaluation of the counter-based normal generator (tests). */
 float dp_normal_host(uint64_t seed, uint64_t sample, uint32_t stream, uint32_t pixel, int c);
 
-/* Number of kernels one UNet evaluation launches (for bench accounting). */
+/* Number of kernels one UNet evaluation launches (dp_unet_forward; also the length of dp_profile_ops' arrays). */
 int dp_launches_per_eval(const dp_engine* e);
+/* Number of kernels one loop step launches (UNet evaluation + update). When the output conv's epilogue applies the update
+ * (the C -> 3|6 conv on the narrow tcgen05 tile) this is dp_launches_per_eval - 1: no update kernel, no step-counter kernel. */
+int dp_launches_per_step(const dp_engine* e);
 
 /* How many of the program's GEMM ops run on CTA-pair (tcgen05 cta_group::2) tiles (tests / reporting). */
 int dp_gemm_pair_count(const dp_engine* e);

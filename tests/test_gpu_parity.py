@@ -105,7 +105,7 @@ def test_full_model_trajectory_vs_oracle():
 
 
 def test_pair_tiles_in_the_full_model_match_single_cta_tiles_and_oracle():
-    """At B=96 the 32x32 and 16x16 convolutions of the CIFAR-10 model run on CTA-pair (cta_group::2) tiles, at B=2 on
+    """At B=96 the 32x32 and 16x16 convolutions of the CIFAR-10 model run on CTA-pair (cta_group::2) tiles, at B=2 mostly on
     single-CTA tiles: the first two samples must agree with the B=2 engine and with the oracle."""
     cfg = O.CIFAR10_CFG
     sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
@@ -122,7 +122,7 @@ def test_pair_tiles_in_the_full_model_match_single_cta_tiles_and_oracle():
     y2 = e2.unet_forward(x[:2].cuda(), labels[:2].cuda()).cpu()
     n2 = e2.pair_gemms
     e2.close()
-    assert n96 >= 40 and n2 == 0, (n96, n2)
+    assert n96 >= 40 and n2 < n96, (n96, n2)   # at B=2 only the fused-GroupNorm GEMMs (whole sample per pair) use pairs
     assert rel(y96[:2], y) < TOL_EVAL, rel(y96[:2], y)
     assert rel(y96[:2], y2) < 1e-3, rel(y96[:2], y2)      # same arithmetic, different tiling
     assert torch.isfinite(y96).all()
