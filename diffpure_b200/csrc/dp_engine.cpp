@@ -80,6 +80,7 @@ struct dp_engine {
   int g_in_channels = 0;
   float* gn_ss = nullptr;            // [B][2][C] scale/shift scratch shared by all GroupNorm ops (stream-ordered)
   size_t gn_ss_floats = 0;
+  void* xg = nullptr;                // super-pair exchange scratch of the fused-GroupNorm GEMMs: data | flags | epoch
   float* bwd_part = nullptr;         // scratch of the GroupNorm backward partial sums (stream-ordered, shared by all ops)
   size_t bwd_part_floats = 0;
   int* d_step = nullptr;
@@ -325,6 +326,7 @@ void dp_destroy(dp_engine* e) {
   cudaFree(e->eps_out);
   cudaFree(e->cond_per_sample);
   cudaFree(e->g_in);
+  cudaFree(e->xg);
   cudaFree(e->gn_ss);
   cudaFree(e->bwd_part);
   cudaFree(e->d_step);
@@ -476,7 +478,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
       n.out_bf16 = d->gn_out_bf16;
       return dp_op_gn_apply(e, &n);
     }
-    if (hw == 1024) { gn_tpg = 4; gn_stages = 4; }
+    if (hw == 1024) { gn_tpg = 2; gn_stages = 4; }  // two CTA pairs per sample, two 256-row tiles each (see GemmParams::upc)
   }
   Op op;
   op.kind = OP_GEMM;
@@ -489,6 +491,18 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     p.gn_gamma = d->gn_gamma; p.gn_beta = d->gn_beta;
     p.gn_cpg = d->N / d->gn_groups; p.gn_hw = hw; p.gn_eps = d->gn_eps; p.gn_silu = d->gn_silu;
     p.tpg = gn_tpg; p.acc_stages = gn_stages;
+    if (hw == 1024) {
+      constexpr size_t kSlots = 128, kData = kSlots * 2 * 4 * 64 * 2 * sizeof(float), kFlags = kSlots * 4 * 8;
+      if (!e->xg) {
+        DP_CUDA(e, cudaSetDevice(e->device));
+        DP_CUDA(e, cudaMalloc(&e->xg, kData + kFlags + 64));
+        DP_CUDA(e, cudaMemset(e->xg, 0, kData + kFlags + 64));
+      }
+      p.upc = 2;
+      p.xg_data = static_cast<float*>(e->xg);
+      p.xg_flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(e->xg) + kData);
+      p.xg_epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(e->xg) + kData + kFlags);
+    }
   }
   long long kprobe = 0;
   for (int sgi = 0; sgi < d->nseg; ++sgi) kprobe += static_cast<long long>(d->a[sgi].taps) * d->a[sgi].C;
@@ -582,7 +596,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     if (gn_fused && hw >= 256) {  // the sample spans the pair's two CTAs: pairs are part of the algorithm, not a heuristic
       if (!dp::gemm_pair_supported(p, bn, op.softmax)) return fail(e, DP_ERR_STATE, "gemm: fused GroupNorm needs CTA pairs");
       op.cg = 2;
-      p.gn_xchg = 1;
+      p.gn_xchg = hw == 256 ? 1 : 0;  // 16x16: DSMEM exchange inside the pair; 32x32: all four CTAs of the super-pair through global memory
     }
   }
   p.num_stages = dp::gemm_max_stages(bn, op.cg, p.gn_out != nullptr);

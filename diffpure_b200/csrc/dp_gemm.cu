@@ -26,8 +26,10 @@ namespace {
 
 // 4 control warps + epilogue warps: BN = 128 -> 8 (two per TMEM lane quadrant, 5 smem stages);
 // BN = 256 -> 4 (keeps the 4th 48 KiB pipeline stage, which matters more there; measured)
-__host__ __device__ constexpr int epi_warps(int bn) { return bn == 128 ? 8 : 4; }
-__host__ __device__ constexpr int num_threads(int bn) { return 128 + 32 * epi_warps(bn); }
+// (the fused-GroupNorm epilogue walks every accumulator twice: always 8 warps -- with 4 the BN = 256 tile was epilogue bound,
+//  138 vs 92 us on the 16x16 256->256 convolution)
+__host__ __device__ constexpr int epi_warps(int bn, bool gn = false) { return (bn == 128 || gn) ? 8 : 4; }
+__host__ __device__ constexpr int num_threads(int bn, bool gn = false) { return 128 + 32 * epi_warps(bn, gn); }
 constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kStgPitch = 36;  // floats; 144-byte rows keep float4 accesses aligned and conflict-free
 
@@ -35,18 +37,18 @@ constexpr int kMaxStages = 8;
 
 // CG = CTAs per tile: 1, or 2 = a CTA pair (cluster of two SMs of one TPC) working on a 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and BN/2 rows of B.
-template <int BN, int CG = 1>
+template <int BN, int CG = 1, bool GN = false>
 struct Smem {
   static constexpr int kStageBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
-  static constexpr int kStagingFloats = epi_warps(BN) * 32 * kStgPitch;
+  static constexpr int kStagingFloats = epi_warps(BN, GN) * 32 * kStgPitch;
   static constexpr int kStatsFloats = 8 * BN * 2;
   // fused-GroupNorm kernels only: scale/shift table [8 segments][BN][2], group statistics [8][BN/4][2],
   // pair exchange buffers [2 parities][BN][2]
   static constexpr int kGnFloats = 8 * BN * 2 + 8 * (BN / 4) * 2 + 2 * BN * 2;
   static constexpr int kBarBytes = 256;
-  static constexpr size_t total(int stages, bool gn = false) {
-    return static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 + (gn ? kGnFloats * 4 : 0) +
+  static constexpr size_t total(int stages) {
+    return static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 + (GN ? kGnFloats * 4 : 0) +
            kBarBytes;
   }
 };
@@ -56,14 +58,15 @@ struct Tile {
   int bo, hd;  // outer batch entry, head
 };
 
-// A work unit u enumerates (batch, M group, N tile); an M group is `tpg` consecutive M units (all of one sample when
-// tpg > 1), an M unit is `cg` consecutive 128-row tiles, CTA `rank` of the pair owns one. j = tile within the unit.
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int u, int j, int cg = 1, int rank = 0) {
+// A work unit u enumerates (batch, M group, N tile); an M group is `upc * tpg` consecutive M units (all of one sample when
+// that is > 1: CTA pair `sub` of the unit's `upc` pairs takes `tpg` of them), an M unit is `cg` consecutive 128-row tiles,
+// CTA `rank` of the pair owns one. j = tile within the pair's share of the unit.
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int u, int j, int cg = 1, int rank = 0, int sub = 0) {
   Tile c;
   c.nt = u % p.n_tiles;
   const int r = u / p.n_tiles;
-  const int m_groups = p.m_tiles / (cg * p.tpg);
-  c.mt = ((r % m_groups) * p.tpg + j) * cg + rank;
+  const int m_groups = p.m_tiles / (cg * p.tpg * p.upc);
+  c.mt = (((r % m_groups) * p.upc + sub) * p.tpg + j) * cg + rank;
   c.b = r / m_groups;
   c.bo = c.b / p.inner;
   c.hd = c.b - c.bo * p.inner;
@@ -82,6 +85,14 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int u, int j, i
 
 // x * sigmoid(x) with ex2.approx + rcp.approx (2 MUFU ops; relative error ~1e-6, far below the bf16 rounding that follows)
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x * sigmoid(x) = h + h tanh(h), h = x / 2: ONE MUFU op (tanh.approx, relative error ~2^-11, far below the bf16 rounding
+// that follows). The fused-GroupNorm epilogue is MUFU bound with the two-op form (32 columns x 32 lanes per block).
+__device__ __forceinline__ float silu_tanh(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // Epilogue feature mask. The common combinations are compiled as specialisations (branch-free inner loop);
 // anything else runs the E_GENERIC instantiation, which tests the same flags at run time.
@@ -90,8 +101,8 @@ constexpr int E_BIAS_N = 1, E_BIAS_M = 2, E_ROWVEC = 4, E_ROWSCALE = 8, E_RESID 
               E_SOFTMAX = 1 << 15;
 
 template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using L = Smem<BN, CG>;
+__global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using L = Smem<BN, CG, (EPI & E_GN) != 0>;
   static_assert(CG == 1 || CG == 2, "CTAs per tile");
   static_assert(CG == 1 || (EPI & E_SOFTMAX) == 0, "the softmax epilogue is single-CTA");
   constexpr bool kSoftmax = (EPI & E_SOFTMAX) != 0;
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   const int stages = p.num_stages;
   float* staging = reinterpret_cast<float*>(sm + static_cast<size_t>(stages) * L::kStageBytes);
   float* sstats = staging + L::kStagingFloats;
-  constexpr int EW = epi_warps(BN);
+  constexpr int EW = epi_warps(BN, kGN);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sstats + L::kStatsFloats + (kGN ? L::kGnFloats : 0));
   const uint32_t bar0 = smem_u32(bars);
   // barrier map (8 bytes each): full[0..8) empty[8..16) tfull[16..20) tempty[20..24) xchg[24..26) ; holder at 26
@@ -154,10 +165,13 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   pdl_entry();
 
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int work0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int work_stride = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // CTA pair index -> (work slot, pair within the unit): upc == 2 groups adjacent pairs into super-pairs
+  const int pair_idx = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int sub = p.upc == 2 ? (pair_idx & 1) : 0;
+  const int work0 = p.upc == 2 ? (pair_idx >> 1) : pair_idx;
+  const int work_stride = (CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x)) / p.upc;
   const int tpg = p.tpg;
-  const int total_units = (p.m_tiles / (CG * tpg)) * p.n_tiles * p.batch;
+  const int total_units = (p.m_tiles / (CG * tpg * p.upc)) * p.n_tiles * p.batch;
   const int ns_mask = p.acc_stages - 1;                 // accumulator stage of the it-th tile = it & ns_mask,
   const int ns_shift = p.acc_stages == 4 ? 2 : 1;       // its barrier parity = (it >> ns_shift) & 1
   int num_kb = 0;
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
       uint32_t phase = 0;
       for (int u = work0; u < total_units; u += work_stride)
       for (int tj = 0; tj < tpg; ++tj) {
-        const Tile c = decode_tile(p, u, tj, CG, rank);
+        const Tile c = decode_tile(p, u, tj, CG, rank, sub);
         int kglobal = 0;
         const int brow = c.nt * BN + rank * (BN / CG) + c.bo * p.b_batch_rows + c.hd * p.b_inner_rows;
         const int a_k0 = c.hd * p.a_inner_k;
@@ -590,6 +604,17 @@ __global__ void __launch_bounds__(num_threads(BN), 1) gemm_kernel(const __grid_c
   tc_fence_before_sync();
   if constexpr (CG == 2) cluster_sync_all();  // no CTA of the pair may exit while its peer can still signal it
   else __syncthreads();
+  if constexpr (kGN) {
+    // super-pair exchange: every CTA has read the launch epoch; the last CTA to finish advances it, so tokens published
+    // during this launch can never satisfy a later launch's waits
+    if (threadIdx.x == 0 && p.upc == 2) {
+      __threadfence();
+      if (atomicAdd(p.xg_epoch + 1, 1ull) == static_cast<unsigned long long>(gridDim.x) - 1) {
+        p.xg_epoch[1] = 0;
+        p.xg_epoch[0] = p.xg_epoch[0] + 1;
+      }
+    }
+  }
   if constexpr (kUpdate) {
     // every thread of this CTA has read the step counter; the last CTA to get here advances it for the next replay
     if (threadIdx.x == 0 && p.upd_arrive != nullptr) {
@@ -613,19 +638,23 @@ int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   const int total = (p.m_tiles / p.tpg) * p.n_tiles * p.batch;  // work units
   if (total <= 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
-  const size_t smem = Smem<BN>::total(p.num_stages, (EPI & E_GN) != 0);
-  return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 1>, dim3(grid), dim3(num_threads(BN)), smem, stream, 1, p));
+  constexpr bool gn = (EPI & E_GN) != 0;
+  const size_t smem = Smem<BN, 1, gn>::total(p.num_stages);
+  return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 1>, dim3(grid), dim3(num_threads(BN, gn)), smem, stream, 1, p));
 }
 
 // CTA-pair launch: clusters of two CTAs, one pair per TPC
 template <int BN, int EPI>
 int launch_pair_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  if (p.tpg < 1 || (p.m_tiles % (2 * p.tpg))) return static_cast<int>(cudaErrorInvalidValue);
-  const int total = (p.m_tiles / (2 * p.tpg)) * p.n_tiles * p.batch;
+  const int upc = p.upc == 2 ? 2 : 1;
+  if (p.tpg < 1 || (p.m_tiles % (2 * p.tpg * upc))) return static_cast<int>(cudaErrorInvalidValue);
+  const int total = (p.m_tiles / (2 * p.tpg * upc)) * p.n_tiles * p.batch;  // work units
   if (total <= 0) return static_cast<int>(cudaErrorInvalidValue);
-  const int pairs = total < num_sms / 2 ? total : num_sms / 2;
-  return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 2>, dim3(2 * pairs), dim3(num_threads(BN)),
-                                   Smem<BN, 2>::total(p.num_stages, (EPI & E_GN) != 0), stream, 2, p));
+  const int slots = num_sms / (2 * upc);                                     // CTA pairs (super-pairs) that fit
+  const int pairs = upc * (total < slots ? total : slots);
+  constexpr bool gn = (EPI & E_GN) != 0;
+  return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 2>, dim3(2 * pairs), dim3(num_threads(BN, gn)),
+                                   Smem<BN, 2, gn>::total(p.num_stages), stream, 2, p));
 }
 
 // epilogues of the convolutions, the only ops big enough for CTA pairs
@@ -700,8 +729,12 @@ int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 size_t gemm_smem_bytes(int bn, int stages, int cg, bool gn) {
-  if (cg == 2) return bn == 256 ? Smem<256, 2>::total(stages, gn) : Smem<128, 2>::total(stages, gn);
-  return bn == 256 ? Smem<256>::total(stages, gn) : (bn == 32 ? Smem<32>::total(stages, gn) : Smem<128>::total(stages, gn));
+  if (gn) {
+    if (cg == 2) return bn == 256 ? Smem<256, 2, true>::total(stages) : Smem<128, 2, true>::total(stages);
+    return bn == 256 ? Smem<256, 1, true>::total(stages) : Smem<128, 1, true>::total(stages);
+  }
+  if (cg == 2) return bn == 256 ? Smem<256, 2>::total(stages) : Smem<128, 2>::total(stages);
+  return bn == 256 ? Smem<256>::total(stages) : (bn == 32 ? Smem<32>::total(stages) : Smem<128>::total(stages));
 }
 
 int gemm_max_stages(int bn, int cg, bool gn) {
@@ -738,16 +771,16 @@ int gemm_init() {
 #undef X
   // fused GroupNorm epilogue
   e = cudaFuncSetAttribute(gemm_kernel<128, E_GN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(Smem<128>::total(gemm_max_stages(128, 1, true), true)));
+                           static_cast<int>(gemm_smem_bytes(128, gemm_max_stages(128, 1, true), 1, true)));
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(gemm_kernel<256, E_GN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(Smem<256>::total(gemm_max_stages(256, 1, true), true)));
+                           static_cast<int>(gemm_smem_bytes(256, gemm_max_stages(256, 1, true), 1, true)));
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(gemm_kernel<128, E_GN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(Smem<128, 2>::total(gemm_max_stages(128, 2, true), true)));
+                           static_cast<int>(gemm_smem_bytes(128, gemm_max_stages(128, 2, true), 2, true)));
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(gemm_kernel<256, E_GN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(Smem<256, 2>::total(gemm_max_stages(256, 2, true), true)));
+                           static_cast<int>(gemm_smem_bytes(256, gemm_max_stages(256, 2, true), 2, true)));
   if (e != cudaSuccess) return static_cast<int>(e);
   // narrow-N tile (output conv, N <= 32): only the plain bias epilogue and the generic fallback
   e = cudaFuncSetAttribute(gemm_kernel<32, E_BIAS_N | E_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -803,6 +836,7 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn, int c
   if (p.batch <= 0) p.batch = 1;
   if (p.inner <= 0) p.inner = 1;
   if (p.tpg <= 0) p.tpg = 1;
+  if (p.upc != 2) p.upc = 1;
   if (p.acc_stages != 4) p.acc_stages = 2;
   p.num_stages = gemm_max_stages(bn, cg, p.gn_out != nullptr);
 }
@@ -813,7 +847,8 @@ int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStre
     // work unit resident in TMEM
     if (softmax || p.resid || p.rowscale || p.bias_along_m || p.silu || p.out_f32 || p.out_bf16 || p.stats ||
         p.alpha != 1.0f || (bn != 128 && bn != 256) || p.N % bn || p.gn_cpg <= 0 || bn % p.gn_cpg || p.gn_cpg > 32 ||
-        p.tpg > p.acc_stages || p.acc_stages * bn > 512)
+        p.tpg > p.acc_stages || p.acc_stages * bn > 512 ||
+        (p.upc == 2 && (cg != 2 || !p.xg_data || !p.xg_flag || !p.xg_epoch || p.stat_nseg != 1 || p.gn_xchg)))
       return static_cast<int>(cudaErrorInvalidValue);
     if (cg == 2) return bn == 256 ? launch_pair_t<256, E_GN>(p, num_sms, stream) : launch_pair_t<128, E_GN>(p, num_sms, stream);
     return bn == 256 ? launch_t<256, E_GN>(p, num_sms, stream) : launch_t<128, E_GN>(p, num_sms, stream);

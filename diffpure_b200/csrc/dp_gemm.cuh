@@ -71,8 +71,11 @@ struct GemmParams {
   float softmax_scale;
   float* rowsum_out;  // [batch*M]
   // ---- accumulator staging ----
-  int tpg;         // tiles per work unit: consecutive M units of ONE sample handled by the same CTA / pair (1 unless the
-                   // fused GroupNorm epilogue needs a whole 32x32 sample resident in TMEM: 4 pair tiles)
+  int tpg;         // tiles per work unit and CTA pair: consecutive M units of ONE sample (1 unless the fused GroupNorm
+                   // epilogue keeps a 32x32 sample resident in TMEM)
+  int upc;         // CTA pairs per work unit (1; 2 = a "super-pair": two adjacent CTA pairs share one 32x32 sample, two
+                   // 256-row tiles each, so that half of every SM's TMEM stays free for the next sample's MMAs while the
+                   // statistics are exchanged -- through global memory, pairs of different clusters share no DSMEM)
   int acc_stages;  // TMEM accumulator stages (2; 4 = all 512 columns with BN = 128)
   // ---- fused GroupNorm(+SiLU) output (E_GN kernels): gn_out = act(GN(acc + bias + rowvec)) as bf16, nothing else ----
   // The statistics of a sample need every row of the sample: its tiles stay in TMEM (tpg stages), pass 1 reduces the
@@ -84,7 +87,11 @@ struct GemmParams {
   int gn_hw;              // rows per sample
   float gn_eps;
   int gn_silu;
-  int gn_xchg;            // 1: a sample spans both CTAs of the pair
+  int gn_xchg;            // 1: a sample spans both CTAs of the pair (upc == 1)
+  // super-pair exchange (upc == 2), engine-owned, shared by all launches of a stream:
+  float* xg_data;         // [super-pairs][2 parities][4 CTAs][BN / cpg groups][2] partial (sum, sum of squares)
+  unsigned long long* xg_flag;   // [super-pairs][4 CTAs]: token of the last unit each CTA published (64-bit: never wraps)
+  unsigned long long* xg_epoch;  // [0] launch epoch (tokens of earlier launches are always smaller), [1] CTA arrival counter
   // ---- fused per-step update (E_UPDATE kernel: the C -> 3|6 output conv, BN = 32): the epilogue applies the SDE / DDPM
   // update to the state instead of writing eps, draws the noise, and the last CTA advances the step counter ----
   float* upd_x;             // state, NHWC fp32 [B*H*W, 3]; null = plain epilogue

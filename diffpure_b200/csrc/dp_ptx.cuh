@@ -183,6 +183,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// GPU-scope release / acquire on a global flag (hand-off between CTAs of different clusters)
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 // Remote shared-memory store that signals the destination CTA's mbarrier with the bytes written (async proxy, like a TMA
 // load: a thread that observes the barrier phase complete sees the data; no fence on the sending side).
 __device__ __forceinline__ void st_async_v2_f32(uint32_t cluster_dst, float a, float b, uint32_t cluster_bar) {

@@ -106,8 +106,16 @@ static void run_conv(const ConvCase& cs) {
     p.gn_out = d_outb;
     p.gn_gamma = d_gamma; p.gn_beta = d_beta;
     p.gn_cpg = N / groups; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
-    if (H * W == 1024) { p.tpg = 4; p.acc_stages = 4; }
-    p.gn_xchg = (cg == 2 && H * W >= 256) ? 1 : 0;
+    if (H * W == 1024) {  // super-pair: two CTA pairs per sample, exchange through global memory
+      p.tpg = 2; p.upc = 2; p.acc_stages = 4;
+      static void* xg = nullptr;
+      const size_t kData = 128 * 2 * 4 * 64 * 2 * sizeof(float), kFlags = 128 * 4 * 8;
+      if (!xg) { CK(cudaMalloc(&xg, kData + kFlags + 64)); CK(cudaMemset(xg, 0, kData + kFlags + 64)); }
+      p.xg_data = static_cast<float*>(xg);
+      p.xg_flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData);
+      p.xg_epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData + kFlags);
+    }
+    p.gn_xchg = (cg == 2 && H * W == 256) ? 1 : 0;
   }
   dp::gemm_fill_geometry(p, B, H, W, N, cs.bn, cg);
   const int nsegs_total = p.m_tiles * p.stat_nseg;
@@ -366,8 +374,16 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
     p.out_f32 = nullptr; p.out_bf16 = nullptr; p.stats = nullptr;
     p.gn_out = reinterpret_cast<__nv_bfloat16*>(d_out);
     p.gn_gamma = d_bias; p.gn_beta = d_bias; p.gn_cpg = N / 32; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
-    if (H * W == 1024) { p.tpg = 4; p.acc_stages = 4; }
-    p.gn_xchg = (cg == 2 && H * W >= 256) ? 1 : 0;
+    if (H * W == 1024) {
+      p.tpg = 2; p.upc = 2; p.acc_stages = 4;
+      void* xg = nullptr;
+      const size_t kData = 128 * 2 * 4 * 64 * 2 * sizeof(float), kFlags = 128 * 4 * 8;
+      CK(cudaMalloc(&xg, kData + kFlags + 64)); CK(cudaMemset(xg, 0, kData + kFlags + 64));
+      p.xg_data = static_cast<float*>(xg);
+      p.xg_flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData);
+      p.xg_epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData + kFlags);
+    }
+    p.gn_xchg = (cg == 2 && H * W == 256) ? 1 : 0;
     dp::gemm_fill_geometry(p, B, H, W, N, bn, cg);
   }
   int sh = 0; while ((1 << sh) < H * W) ++sh;
@@ -435,7 +451,7 @@ int main(int argc, char** argv) {
       {"pair conv3x3 s2 32->16 128",   2, 16, 16, 128, 9,  0, 128, 128, 2, true, false,false,false,true, false, 1.f, 2},
       {"pair conv 64x64 many tiles",   20, 64, 64, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f, 2},
       // fused GroupNorm + SiLU epilogue: the sample's accumulators resident in TMEM, two passes
-      {"gn pair 32x32 128->128 (4 resident tiles, pair exchange)", 3, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn super-pair 32x32 128->128 (global exchange)", 3, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn pair 32x32 256->256 (two N tiles)",                    2, 32, 32, 256, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn pair 32x32 many samples",                              40, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn pair 16x16 256->256 bn256 (pair exchange)",            5, 16, 16, 256, 9, 0, 256, 256, 1, true, true, false,false,false,true, 1.f, 2, 1},
