@@ -611,6 +611,87 @@ int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nh
   return static_cast<int>(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused pre / post steps either side of the loop (eval_sde_adv.py:73-89: [0,1] -> [-1,1], ImageNet 224 <-> 256 bilinear
+// resize; utils.py:144-153: classifier normalisation). Bilinear = F.interpolate(mode='bilinear', align_corners=False):
+// src = scale (dst + 0.5) - 0.5 clamped at 0, scale = in / out, in fp32 and in ATen's association order.
+// ------------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_of(int dst, int in_size, int out_size) {
+  Lerp r;
+  if (in_size == out_size) { r.i0 = r.i1 = dst; r.l0 = 1.f; r.l1 = 0.f; return r; }
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  r.i0 = static_cast<int>(src);
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - static_cast<float>(r.i0);
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+// x_state[b,h,w,c] = sx * map(resize(x0))[b,c,h,w] + se * noise     (x0: NCHW [B,C,Hin,Win])
+__global__ void init_state_pre_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                      float* __restrict__ x, int B, int C, int H, int W, int Hin, int Win, int unit_range,
+                                      float sx, float se, unsigned long long seed, unsigned long long sample_offset) {
+  pdl_entry();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  const long long n = static_cast<long long>(B) * C * HW;
+  if (i >= n) return;
+  const int pix = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+  const int h = pix / W, w = pix - h * W;
+  const Lerp ly = lerp_of(h, Hin, H), lx = lerp_of(w, Win, W);
+  const float* src = x0 + (static_cast<size_t>(b) * C + c) * Hin * Win;
+  float v = ly.l0 * (lx.l0 * src[ly.i0 * Win + lx.i0] + lx.l1 * src[ly.i0 * Win + lx.i1]) +
+            ly.l1 * (lx.l0 * src[ly.i1 * Win + lx.i0] + lx.l1 * src[ly.i1 * Win + lx.i1]);
+  if (unit_range) v = (v - 0.5f) * 2.f;
+  const float e = noise ? noise[i] : dp_normal(seed, sample_offset + b, 0u, static_cast<unsigned>(pix), c);
+  x[(static_cast<size_t>(b) * HW + pix) * C + c] = sx * v + se * e;
+}
+
+int launch_init_state_pre(const float* x0_nchw, const float* noise_nchw, float* x_nhwc, int B, int C, int H, int W,
+                          int Hin, int Win, int unit_range, float sx, float se, unsigned long long seed,
+                          unsigned long long sample_offset, cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * C * H * W;
+  init_state_pre_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x0_nchw, noise_nchw, x_nhwc, B, C, H, W,
+                                                                              Hin, Win, unit_range, sx, se, seed,
+                                                                              sample_offset);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// out[b,c,ho,wo] = ((resize(x)[b,c,ho,wo] + 1) / 2 - mean[c]) / std[c]      (x: NHWC [B,H,W,C], out: NCHW)
+__global__ void final_post_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int H, int W,
+                                  int Ho, int Wo, PostParams pp) {
+  pdl_entry();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * C * Ho * Wo;
+  if (i >= n) return;
+  const int wo = static_cast<int>(i % Wo);
+  const int ho = static_cast<int>((i / Wo) % Ho);
+  const int c = static_cast<int>((i / (static_cast<long long>(Wo) * Ho)) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(Wo) * Ho * C));
+  const Lerp ly = lerp_of(ho, H, Ho), lx = lerp_of(wo, W, Wo);
+  const float* src = x + static_cast<size_t>(b) * H * W * C + c;
+  float v = ly.l0 * (lx.l0 * src[(ly.i0 * W + lx.i0) * C] + lx.l1 * src[(ly.i0 * W + lx.i1) * C]) +
+            ly.l1 * (lx.l0 * src[(ly.i1 * W + lx.i0) * C] + lx.l1 * src[(ly.i1 * W + lx.i1) * C]);
+  if (pp.unit_range) v = (v + 1.f) * 0.5f;
+  if (pp.std[0] != 0.f) v = (v - pp.mean[c]) / pp.std[c];
+  out[i] = v;
+}
+
+int launch_final_post(const float* x_nhwc, float* out_nchw, int B, int C, int H, int W, int Ho, int Wo,
+                      const PostParams& pp, cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * C * Ho * Wo;
+  final_post_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x_nhwc, out_nchw, B, C, H, W, Ho, Wo, pp);
+  return static_cast<int>(cudaGetLastError());
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
   pdl_entry();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

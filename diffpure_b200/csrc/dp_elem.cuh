@@ -80,6 +80,17 @@ int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nh
                       float sx, float se, unsigned long long seed, unsigned long long sample_offset,
                       cudaStream_t s);
 int launch_nhwc_to_nchw(const float* x_nhwc, float* out_nchw, int B, int C, int HW, cudaStream_t s);
+// Fused pre / post steps of the caller (eval_sde_adv.py:73-89, utils.py:144-153): bilinear resize (align_corners = False)
+// + [0,1] -> [-1,1] in front of the forward diffusion; resize + [-1,1] -> [0,1] + classifier normalisation behind the loop.
+struct PostParams {
+  int unit_range;
+  float mean[3], std[3];  // std[0] == 0: no normalisation
+};
+int launch_init_state_pre(const float* x0_nchw, const float* noise_nchw, float* x_nhwc, int B, int C, int H, int W,
+                          int Hin, int Win, int unit_range, float sx, float se, unsigned long long seed,
+                          unsigned long long sample_offset, cudaStream_t s);
+int launch_final_post(const float* x_nhwc, float* out_nchw, int B, int C, int H, int W, int Ho, int Wo,
+                      const PostParams& pp, cudaStream_t s);
 int launch_step_advance(int* step, cudaStream_t s);
 
 // ---- data-gradient kernels (dp_bwd.cu) ---------------------------------------------------------------------------------

@@ -943,8 +943,17 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
   DP_CUDA(e, cudaEventRecord(e->staging_done, s));
   DP_CUDA(e, cudaMemsetAsync(e->d_step, 0, 2 * sizeof(int), s));  // step counter + the CTA arrival counter beside it
   const int HW = e->H * e->W;
-  int rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
-                                 p->seed, p->sample_offset, s);
+  int rc;
+  if (p->in_h < 0 || p->in_w < 0 || p->out_h < 0 || p->out_w < 0 || (p->in_h == 0) != (p->in_w == 0) ||
+      (p->out_h == 0) != (p->out_w == 0))
+    return fail(e, DP_ERR_INVALID, "pre / post grids: give both extents or neither");
+  if (p->in_h || p->in_unit_range)
+    rc = dp::launch_init_state_pre(x0_nchw, p->init_noise, e->x_state, e->B, 3, e->H, e->W, p->in_h ? p->in_h : e->H,
+                                   p->in_w ? p->in_w : e->W, p->in_unit_range, p->init_scale_x, p->init_scale_e, p->seed,
+                                   p->sample_offset, s);
+  else
+    rc = dp::launch_init_state(x0_nchw, p->init_noise, e->x_state, e->B, 3, HW, p->init_scale_x, p->init_scale_e,
+                               p->seed, p->sample_offset, s);
   if (rc) return fail(e, DP_ERR_CUDA, "init_state launch failed");
   if (p->states) {
     rc = dp::launch_nhwc_to_nchw(e->x_state, p->states, e->B, 3, HW, s);
@@ -959,8 +968,16 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
     }
   }
   for (int i = 0; i < p->steps; ++i) DP_CUDA(e, cudaGraphLaunch(e->g_step, s));
-  rc = dp::launch_nhwc_to_nchw(e->x_state, out_nchw, e->B, 3, HW, s);
-  if (rc) return fail(e, DP_ERR_CUDA, "nhwc_to_nchw launch failed");
+  if (p->out_h || p->out_unit_range || p->out_std[0] != 0.f) {
+    dp::PostParams pp;
+    pp.unit_range = p->out_unit_range;
+    for (int i = 0; i < 3; ++i) { pp.mean[i] = p->out_mean[i]; pp.std[i] = p->out_std[i]; }
+    rc = dp::launch_final_post(e->x_state, out_nchw, e->B, 3, e->H, e->W, p->out_h ? p->out_h : e->H,
+                               p->out_w ? p->out_w : e->W, pp, s);
+  } else {
+    rc = dp::launch_nhwc_to_nchw(e->x_state, out_nchw, e->B, 3, HW, s);
+  }
+  if (rc) return fail(e, DP_ERR_CUDA, "final layout launch failed");
   if (!stream) DP_CUDA(e, cudaStreamSynchronize(s));
   return DP_OK;
 }

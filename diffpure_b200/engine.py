@@ -272,8 +272,9 @@ class Engine:
         st = torch.cuda.current_stream(self._dev()).cuda_stream
         return C.c_void_p(st) if st else None
 
-    def _prep(self, x):
-        assert x.shape == (self.B, 3, self.H, self.W), (tuple(x.shape), (self.B, 3, self.H, self.W))
+    def _prep(self, x, hw=None):
+        want = (self.B, 3) + (tuple(hw) if hw else (self.H, self.W))
+        assert tuple(x.shape) == want, (tuple(x.shape), want)
         return x.to(device=self._dev(), dtype=torch.float32).contiguous()
 
     def unet_forward(self, x, cond):
@@ -301,33 +302,43 @@ class Engine:
         return out
 
     def purify(self, x0, cond, coef, init_scale_x, init_scale_e, *, update_kind=_lib.DP_UPDATE_LINEAR,
-               init_noise=None, step_noise=None, seed=0, sample_offset=0, anchor=None, states=None):
+               init_noise=None, step_noise=None, seed=0, sample_offset=0, anchor=None, states=None,
+               in_unit_range=False, out_hw=None, out_unit_range=False, out_norm=None):
         """Runs the whole loop on the device. cond: [steps] host floats; coef: [steps, ncoef] host floats.
-        states: optional [steps+1,B,3,H,W] fp32 device tensor receiving the state before every step and the final one."""
-        x0 = self._prep(x0)
+        states: optional [steps+1,B,3,H,W] fp32 device tensor receiving the state before every step and the final one.
+        Fused pre / post steps (eval_sde_adv.py:73-89): x0 may have another spatial size (bilinear resize to the model
+        grid) and be in [0,1] (in_unit_range); out_hw resizes the result, out_unit_range maps it to [0,1], out_norm =
+        (mean[3], std[3]) applies the classifier's normalisation."""
+        in_hw = tuple(x0.shape[2:]) if tuple(x0.shape[2:]) != (self.H, self.W) else None
+        x0 = self._prep(x0, in_hw)
         cond = np.ascontiguousarray(np.asarray(cond, dtype=np.float32))
         coef = np.ascontiguousarray(np.asarray(coef, dtype=np.float32))
         steps = cond.shape[0]
         assert coef.ndim == 2 and coef.shape[0] == steps
+        model_shape = (self.B, 3, self.H, self.W)
         if init_noise is not None:
             init_noise = init_noise.to(device=self._dev(), dtype=torch.float32).contiguous()
-            assert init_noise.shape == x0.shape
+            assert tuple(init_noise.shape) == model_shape
         if step_noise is not None:
             step_noise = step_noise.to(device=self._dev(), dtype=torch.float32).contiguous()
-            assert step_noise.shape == (steps,) + tuple(x0.shape)
+            assert tuple(step_noise.shape) == (steps,) + model_shape
         if anchor is not None:
             anchor = self._prep(anchor)
-            assert anchor.shape == x0.shape
         if states is not None:
             assert states.is_cuda and states.dtype == torch.float32 and states.is_contiguous() and \
-                states.shape == (steps + 1,) + tuple(x0.shape)
-        out = torch.empty_like(x0)
+                tuple(states.shape) == (steps + 1,) + model_shape
+        out = torch.empty((self.B, 3) + (tuple(out_hw) if out_hw else (self.H, self.W)), device=self._dev(),
+                          dtype=torch.float32)
+        mean, std = out_norm if out_norm is not None else ((0.0,) * 3, (0.0,) * 3)
         p = _lib.PurifyParams(steps, update_kind, coef.shape[1], cond.ctypes.data, coef.ctypes.data,
                               float(init_scale_x), float(init_scale_e),
                               init_noise.data_ptr() if init_noise is not None else None,
                               step_noise.data_ptr() if step_noise is not None else None, int(seed),
                               int(sample_offset), anchor.data_ptr() if anchor is not None else None,
-                              states.data_ptr() if states is not None else None)
+                              states.data_ptr() if states is not None else None,
+                              in_hw[0] if in_hw else 0, in_hw[1] if in_hw else 0, 1 if in_unit_range else 0,
+                              out_hw[0] if out_hw else 0, out_hw[1] if out_hw else 0, 1 if out_unit_range else 0,
+                              (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std]))
         self._keep = (x0, init_noise, step_noise, anchor)    # inputs stay alive until the enqueued work has run
         self._check(self.lib.dp_purify(self.h, x0.data_ptr(), out.data_ptr(), C.byref(p), self._stream()), "dp_purify")
         return out

@@ -102,7 +102,9 @@ class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
                 ("init_noise", C.c_void_p), ("step_noise", C.c_void_p), ("seed", C.c_uint64),
-                ("sample_offset", C.c_uint64), ("anchor", C.c_void_p), ("states", C.c_void_p)]
+                ("sample_offset", C.c_uint64), ("anchor", C.c_void_p), ("states", C.c_void_p),
+                ("in_h", C.c_int), ("in_w", C.c_int), ("in_unit_range", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
+                ("out_unit_range", C.c_int), ("out_mean", C.c_float * 3), ("out_std", C.c_float * 3)]
 
 
 # every symbol include/diffpure_b200.h declares: name -> (restype, argtypes)

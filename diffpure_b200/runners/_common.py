@@ -154,12 +154,42 @@ class PurifyRunner(torch.nn.Module):
         assert img.ndim == 4, img.ndim
         if self.device_from_input:
             dev = img.device if img.device.type == "cuda" else self.device
+        elif self.device.type == "cuda" and self.device.index is None and img.device.type == "cuda":
+            dev = img.device        # a generic 'cuda' device = the caller's current one: nn.DataParallel replicas receive
+                                    # their chunk on their own GPU (eval_sde_adv.py:227-229) and must run there
         else:
             dev = self.device if self.device.type == "cuda" else img.device
         x0 = img.to(dev)
         dump = _Dump(self.args, bs_id, tag)
         dump.image('original_input.png', x0)
         return x0, dev, dump
+
+    _fuse_kw = {}                   # pre / post steps fused into this call's dp_purify (see purify_unit_range)
+
+    def purify_unit_range(self, x01, out_hw=None, out_norm=None, bs_id=2, tag=None, **kw):
+        """The caller's pre / post steps fused into the engine call (SDE_Adv_Model.forward, eval_sde_adv.py:73-89):
+        x01 in [0,1] at any spatial size -> bilinear resize to the model grid, (x - 0.5) * 2, forward diffusion, the loop,
+        bilinear resize to `out_hw`, (x + 1) / 2 and optionally the classifier normalisation `out_norm = (mean, std)`
+        (utils.py:144-153) -- no eager kernels either side of the loop. Needs sample_step == 1 and no image dumps
+        (bs_id >= 2 or save_images off); forward only."""
+        if self.args.sample_step != 1:
+            raise ValueError("purify_unit_range needs sample_step == 1")
+        if torch.is_grad_enabled() and x01.requires_grad:
+            raise ValueError("purify_unit_range is forward-only; use image_editing_sample for gradients")
+        if bs_id < 2 and getattr(self.args, "save_images", True):
+            raise ValueError("purify_unit_range does not write the bs_id < 2 image dumps")
+        self._fuse_kw = dict(in_unit_range=True, out_hw=tuple(out_hw) if out_hw else None, out_unit_range=True,
+                             out_norm=out_norm)
+        try:
+            return self.image_editing_sample(x01, bs_id=bs_id, tag=tag, **kw)
+        finally:
+            self._fuse_kw = {}
+
+    def _init_noise(self, x, init_noise, dev):
+        """The forward-diffusion draw (reference: torch.randn_like(x)); fused calls leave it to the engine's generator."""
+        if init_noise is not None:
+            return init_noise.to(dev)
+        return None if self._fuse_kw else torch.randn_like(x)
 
     def _wants_grad(self, x):
         """True when the caller differentiates through the loop (white-box attacks); raises for networks whose

@@ -46,9 +46,10 @@ class Diffusion(PurifyRunner):
             cond, coef, sx, se = schedule.ddpm_tables(self.args.t, *self._sched, var_type=self.model_var_type)
 
             def one_pass(it, x):
-                e = torch.randn_like(x) if init_noise is None else init_noise.to(dev)
-                dump.image(f'init_{it}.png', x * sx + e * se)
+                e = self._init_noise(x, init_noise, dev)
+                if dump.on:
+                    dump.image(f'init_{it}.png', x * sx + e * se)
                 return eng.purify(x, cond, coef, sx, se, init_noise=e, step_noise=step_noise,
-                                  seed=self._call_seed(seed, it), sample_offset=self.sample_offset)
+                                  seed=self._call_seed(seed, it), sample_offset=self.sample_offset, **self._fuse_kw)
 
             return self._passes(x0, dump, one_pass)

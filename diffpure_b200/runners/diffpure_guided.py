@@ -45,10 +45,11 @@ class GuidedDiffusion(PurifyRunner):
             cond, coef, sx, se = schedule.guided_tables(self.args.t, self.num_timesteps)
 
             def one_pass(it, x):
-                e = torch.randn_like(x) if init_noise is None else init_noise.to(dev)
-                dump.image(f'init_{it}.png', x * sx + e * se)
+                e = self._init_noise(x, init_noise, dev)
+                if dump.on:
+                    dump.image(f'init_{it}.png', x * sx + e * se)
                 return eng.purify(x, cond, coef, sx, se, update_kind=_lib.DP_UPDATE_LEARNED_RANGE, init_noise=e,
                                   step_noise=step_noise, seed=self._call_seed(seed, it),
-                                  sample_offset=self.sample_offset)
+                                  sample_offset=self.sample_offset, **self._fuse_kw)
 
             return self._passes(x0, dump, one_pass)

@@ -54,11 +54,12 @@ class OdeGuidedDiffusion(PurifyRunner):
                 fixed = torch.FloatTensor(1, *x.shape[1:]).normal_(0, 1, generator=torch.manual_seed(self.args.seed))
                 e = fixed.to(dev).repeat(x.shape[0], 1, 1, 1)
             else:
-                e = torch.randn_like(x) if init_noise is None else init_noise.to(dev)
-            dump.image(f'init_{it}.png', (x * sx + e * se).detach())
+                e = self._init_noise(x, init_noise, dev)
+            if dump.on:
+                dump.image(f'init_{it}.png', (x * sx + e * se).detach())
             if self._wants_grad(x):      # odeint_adjoint in the reference (L230-238): here the discrete Euler loop's gradient
                 return PurifyWithGrad.apply(x, None, self.model, cond, coef, sx, se, e, None, 0, self.sample_offset,
                                             _lib.DP_UPDATE_LINEAR)
-            return eng.purify(x, cond, coef, sx, se, init_noise=e, sample_offset=self.sample_offset)
+            return eng.purify(x, cond, coef, sx, se, init_noise=e, sample_offset=self.sample_offset, **self._fuse_kw)
 
         return self._passes(x0, dump, one_pass)

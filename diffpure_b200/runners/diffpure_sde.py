@@ -122,7 +122,7 @@ class RevGuidedDiffusion(PurifyRunner):
         cond, coef = self._tables_for(self.args.t)      # the reverse grid always spans t* (L228-231) ...
 
         def one_pass(it, x):
-            e = torch.randn_like(x) if init_noise is None else init_noise.to(dev)        # L217
+            e = self._init_noise(x, init_noise, dev)                                     # L217
             level = self.args.t
             if self.args.rand_t:                         # ... only the forward-diffusion level is jittered (L219-223)
                 level = self.args.t + np.random.randint(-self.args.t_delta, self.args.t_delta)
@@ -133,8 +133,9 @@ class RevGuidedDiffusion(PurifyRunner):
                 dump.image(f'init_{it}.png', (x * sx + e * se).detach())
                 return PurifyWithGrad.apply(x, None, self.model, cond, coef, sx, se, e, step_noise, s,
                                             self.sample_offset, _lib.DP_UPDATE_LINEAR)
-            dump.image(f'init_{it}.png', x * sx + e * se)
+            if dump.on:
+                dump.image(f'init_{it}.png', x * sx + e * se)
             return eng.purify(x, cond, coef, sx, se, init_noise=e, step_noise=step_noise, seed=s,
-                              sample_offset=self.sample_offset)       # L228-239
+                              sample_offset=self.sample_offset, **self._fuse_kw)       # L228-239
 
         return self._passes(x0, dump, one_pass)

@@ -254,6 +254,13 @@ typedef struct {
   const float* anchor;      /* DP_UPDATE_LINEAR_ANCHORED: device [B,3,H,W] x_init, or NULL -> the (diffused) initial state */
   float* states;            /* optional device [steps+1,B,3,H,W]: the state before every step and the final one (the
                                discretise-then-differentiate backward pass replays the loop from them) */
+  /* Fused pre / post steps of the caller (SDE_Adv_Model.forward, eval_sde_adv.py:73-89; classifier wrappers,
+   * utils.py:144-153). All zero = x0 and out are [B,3,H,W] in [-1,1] (the runner API). */
+  int in_h, in_w;           /* x0 is [B,3,in_h,in_w]: bilinear resize (align_corners = False) to the model grid; 0 = model grid */
+  int in_unit_range;        /* 1: x0 is in [0,1], mapped to [-1,1] after the resize */
+  int out_h, out_w;         /* out is [B,3,out_h,out_w]: bilinear resize of the purified image; 0 = model grid */
+  int out_unit_range;       /* 1: (x + 1) / 2 */
+  float out_mean[3], out_std[3]; /* classifier normalisation (x - mean) / std behind the range map; out_std[0] == 0: none */
 } dp_purify_params;
 
 /* The whole purification loop on the device: forward-diffuse, then `steps` x (UNet + fused update).
