@@ -443,7 +443,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   // ---- fused GroupNorm output: decide whether the sample's accumulators can stay resident in TMEM ----------------
   // HW <= 128: every tile holds whole samples (any tile kind). HW == 256: one CTA-pair tile per sample. HW == 1024: four
   // CTA-pair tiles of BN = 128 = all 512 TMEM columns of both SMs. Anything else (or DP_GEMM_GN=0): the unfused sequence.
-  bool gn_fused = false;
+  bool gn_fused = false, gn_super = false;
   int gn_tpg = 1, gn_stages = 2;
   if (d->gn_out_bf16) {
     if (d->out_f32 || d->out_bf16 || d->stats || d->resid || d->rowscale || d->silu || d->softmax || d->alpha != 1.0f ||
@@ -478,7 +478,12 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
       n.out_bf16 = d->gn_out_bf16;
       return dp_op_gn_apply(e, &n);
     }
-    if (hw == 1024) { gn_tpg = 2; gn_stages = 4; }  // two CTA pairs per sample, two 256-row tiles each (see GemmParams::upc)
+    // 32x32: the sample's four 256-row tiles stay in the four accumulator stages of ONE CTA pair (exchange over DSMEM).
+    // DP_GN_UPC=2 selects the measured alternative, two pairs per sample with half of TMEM free for the next sample: the
+    // exchange then crosses clusters through global memory, whose round trip (possibly across the two dies) cost more than
+    // the overlap won (221 vs 176 us on the 128->128 convolution at B=512).
+    static const int gn_upc = [] { const char* v = std::getenv("DP_GN_UPC"); return v && std::atoi(v) == 2 ? 2 : 1; }();
+    if (hw == 1024) { gn_tpg = gn_upc == 2 ? 2 : 4; gn_stages = 4; gn_super = gn_upc == 2; }
   }
   Op op;
   op.kind = OP_GEMM;
@@ -491,7 +496,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     p.gn_gamma = d->gn_gamma; p.gn_beta = d->gn_beta;
     p.gn_cpg = d->N / d->gn_groups; p.gn_hw = hw; p.gn_eps = d->gn_eps; p.gn_silu = d->gn_silu;
     p.tpg = gn_tpg; p.acc_stages = gn_stages;
-    if (hw == 1024) {
+    if (gn_super) {
       constexpr size_t kSlots = 128, kData = kSlots * 2 * 4 * 64 * 2 * sizeof(float), kFlags = kSlots * 4 * 8;
       if (!e->xg) {
         DP_CUDA(e, cudaSetDevice(e->device));
@@ -596,7 +601,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     if (gn_fused && hw >= 256) {  // the sample spans the pair's two CTAs: pairs are part of the algorithm, not a heuristic
       if (!dp::gemm_pair_supported(p, bn, op.softmax)) return fail(e, DP_ERR_STATE, "gemm: fused GroupNorm needs CTA pairs");
       op.cg = 2;
-      p.gn_xchg = hw == 256 ? 1 : 0;  // 16x16: DSMEM exchange inside the pair; 32x32: all four CTAs of the super-pair through global memory
+      p.gn_xchg = p.upc == 2 ? 0 : 1;  // DSMEM exchange inside the pair (a super-pair's four CTAs go through global memory)
     }
   }
   p.num_stages = dp::gemm_max_stages(bn, op.cg, p.gn_out != nullptr);

@@ -44,8 +44,8 @@ struct Smem {
   static constexpr int kStagingFloats = epi_warps(BN, GN) * 32 * kStgPitch;
   static constexpr int kStatsFloats = 8 * BN * 2;
   // fused-GroupNorm kernels only: scale/shift table [8 segments][BN][2], group statistics [8][BN/4][2],
-  // pair exchange buffers [2 parities][BN][2]
-  static constexpr int kGnFloats = 8 * BN * 2 + 8 * (BN / 4) * 2 + 2 * BN * 2;
+  // pair exchange buffers [2 parities][BN][2], additive table [8 segments][BN]
+  static constexpr int kGnFloats = 8 * BN * 2 + 8 * (BN / 4) * 2 + 2 * BN * 2 + 8 * BN;
   static constexpr int kBarBytes = 256;
   static constexpr size_t total(int stages) {
     return static_cast<size_t>(stages) * kStageBytes + kStagingFloats * 4 + kStatsFloats * 4 + (GN ? kGnFloats * 4 : 0) +

@@ -164,7 +164,7 @@ def golden_adm_and_celeba():
     print("celeba tiny |y|", y.abs().mean().item())
 
 
-if __name__ == "__main__" and "--siblings" not in sys.argv and "--adm-vpsde" not in sys.argv:
+if __name__ == "__main__" and not ({"--siblings", "--adm-vpsde", "--checkpoint-keys"} & set(sys.argv)):
     if "--adm-celeba" not in sys.argv:
         main()
     if "--ncsnpp" not in sys.argv:
@@ -243,3 +243,29 @@ def golden_adm_vpsde():
 
 if __name__ == "__main__" and "--adm-vpsde" in sys.argv:
     golden_adm_vpsde()
+
+
+def golden_checkpoint_keys():
+    """The key sets (ordered names + shapes) of the three real checkpoints the reference loads with strict load_state_dict:
+    pretrained/score_sde/checkpoint_8.pth['model'] (runners/diffpure_sde.py:178-182), pretrained/guided_diffusion/
+    256x256_diffusion_uncond.pt (diffpure_guided.py:31) and celeba_hq.ckpt (diffpure_ddpm.py:72-74) -- i.e. the
+    state_dict() of the reference modules built from the shipped yaml configs. The files themselves do not exist offline."""
+    import json
+    out = {}
+    m, _ = ref_import.build_ncsnpp()
+    out["score_sde/checkpoint_8.pth:model (configs/cifar10.yml)"] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    with torch.device("meta"):
+        adm, _, _ = ref_import.build_adm()
+    out["guided_diffusion/256x256_diffusion_uncond.pt (configs/imagenet.yml)"] = \
+        [[k, list(v.shape)] for k, v in adm.state_dict().items()]
+    with torch.device("meta"):
+        cel, _ = ref_import.build_celeba()
+    out["celeba_hq.ckpt (configs/celeba.yml)"] = [[k, list(v.shape)] for k, v in cel.state_dict().items()]
+    with open(os.path.join(OUT, "checkpoint_keys.json"), "w") as f:
+        json.dump(out, f)
+    for k, v in out.items():
+        print(k, len(v), "tensors", sum(int(np.prod(s)) for _, s in v), "elements")
+
+
+if __name__ == "__main__" and "--checkpoint-keys" in sys.argv:
+    golden_checkpoint_keys()

@@ -106,7 +106,9 @@ static void run_conv(const ConvCase& cs) {
     p.gn_out = d_outb;
     p.gn_gamma = d_gamma; p.gn_beta = d_beta;
     p.gn_cpg = N / groups; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
-    if (H * W == 1024) {  // super-pair: two CTA pairs per sample, exchange through global memory
+    const bool super_pair = strstr(cs.name, "super-pair") != nullptr;
+    if (H * W == 1024 && !super_pair) { p.tpg = 4; p.acc_stages = 4; }  // the sample's four tiles resident in one pair
+    if (H * W == 1024 && super_pair) {  // two CTA pairs per sample, exchange through global memory
       p.tpg = 2; p.upc = 2; p.acc_stages = 4;
       static void* xg = nullptr;
       const size_t kData = 128 * 2 * 4 * 64 * 2 * sizeof(float), kFlags = 128 * 4 * 8;
@@ -115,7 +117,7 @@ static void run_conv(const ConvCase& cs) {
       p.xg_flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData);
       p.xg_epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData + kFlags);
     }
-    p.gn_xchg = (cg == 2 && H * W == 256) ? 1 : 0;
+    p.gn_xchg = (cg == 2 && H * W >= 256 && p.upc != 2) ? 1 : 0;
   }
   dp::gemm_fill_geometry(p, B, H, W, N, cs.bn, cg);
   const int nsegs_total = p.m_tiles * p.stat_nseg;
@@ -374,7 +376,9 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
     p.out_f32 = nullptr; p.out_bf16 = nullptr; p.stats = nullptr;
     p.gn_out = reinterpret_cast<__nv_bfloat16*>(d_out);
     p.gn_gamma = d_bias; p.gn_beta = d_bias; p.gn_cpg = N / 32; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
-    if (H * W == 1024) {
+    const bool super_pair = getenv("DP_GN_UPC") && atoi(getenv("DP_GN_UPC")) == 2;
+    if (H * W == 1024 && !super_pair) { p.tpg = 4; p.acc_stages = 4; }
+    if (H * W == 1024 && super_pair) {
       p.tpg = 2; p.upc = 2; p.acc_stages = 4;
       void* xg = nullptr;
       const size_t kData = 128 * 2 * 4 * 64 * 2 * sizeof(float), kFlags = 128 * 4 * 8;
@@ -383,7 +387,7 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
       p.xg_flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData);
       p.xg_epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(xg) + kData + kFlags);
     }
-    p.gn_xchg = (cg == 2 && H * W == 256) ? 1 : 0;
+    p.gn_xchg = (cg == 2 && H * W >= 256 && p.upc != 2) ? 1 : 0;
     dp::gemm_fill_geometry(p, B, H, W, N, bn, cg);
   }
   int sh = 0; while ((1 << sh) < H * W) ++sh;
@@ -452,6 +456,7 @@ int main(int argc, char** argv) {
       {"pair conv 64x64 many tiles",   20, 64, 64, 64, 9,  0, 128, 128, 1, true, true, false,false,true, false, 1.f, 2},
       // fused GroupNorm + SiLU epilogue: the sample's accumulators resident in TMEM, two passes
       {"gn super-pair 32x32 128->128 (global exchange)", 3, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
+      {"gn pair 32x32 128->128 (4 resident tiles, DSMEM exchange)", 3, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn pair 32x32 256->256 (two N tiles)",                    2, 32, 32, 256, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn pair 32x32 many samples",                              40, 32, 32, 128, 9, 0, 128, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn pair 16x16 256->256 bn256 (pair exchange)",            5, 16, 16, 256, 9, 0, 256, 256, 1, true, true, false,false,false,true, 1.f, 2, 1},
