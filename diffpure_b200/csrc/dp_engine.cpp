@@ -446,31 +446,41 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   bool gn_fused = false, gn_super = false;
   int gn_tpg = 1, gn_stages = 2;
   if (d->gn_out_bf16) {
-    if (d->out_f32 || d->out_bf16 || d->stats || d->resid || d->rowscale || d->silu || d->softmax || d->alpha != 1.0f ||
-        d->bias_along_m || !d->gn_gamma || !d->gn_beta || d->gn_groups <= 0 || d->N % d->gn_groups)
-      return fail(e, DP_ERR_INVALID, "gemm: the fused GroupNorm output takes bias / rowvec only and replaces every other output");
+    const bool late = d->out_f32 != nullptr;   // the result itself is an output too (fp32 residual stream)
+    if (d->rowscale || d->silu || d->softmax || d->bias_along_m || !d->gn_gamma || !d->gn_beta || d->gn_groups <= 0 ||
+        d->N % d->gn_groups)
+      return fail(e, DP_ERR_INVALID, "gemm: fused GroupNorm output: unsupported epilogue combination");
+    if (!late && (d->out_bf16 || d->stats || d->resid || d->alpha != 1.0f))
+      return fail(e, DP_ERR_INVALID, "gemm: a GroupNorm output without out_f32 replaces every other output (bias / rowvec only)");
+    if (late && !d->stats)
+      return fail(e, DP_ERR_INVALID, "gemm: a GroupNorm output next to out_f32 needs the partial-statistics tensor too");
     static const int gn_on = [] { const char* v = std::getenv("DP_GEMM_GN"); return v ? std::atoi(v) : 1; }();
     const int cpg = d->N / d->gn_groups;
     const bool shape_ok = (hw == 16 || hw == 64 || hw == 128 || hw == 256 || hw == 1024) && d->H > 1 && d->N % 128 == 0 &&
                           128 % cpg == 0 && (d->batch <= 1);
-    gn_fused = gn_on && shape_ok;
+    gn_fused = shape_ok && (late ? (gn_on == 1 || gn_on == 2) : gn_on >= 1);  // DP_GEMM_GN: 0 none, 1 all, 3 resident kind only
     if (!gn_fused) {
-      // unfused fallback with engine-owned scratch: raw result in bf16 + partial statistics, then finalize + apply
-      int braw, bst;
-      const size_t rows = static_cast<size_t>(d->B) * hw;
-      if (int rc = dp_buffer_alloc(e, rows * d->N * 2, &braw)) return rc;
-      const size_t srows = hw >= 128 ? rows / 128 : static_cast<size_t>((d->B + 128 / hw - 1) / (128 / hw)) * (128 / hw);
-      if (int rc = dp_buffer_alloc(e, srows * d->N * 2 * sizeof(float), &bst)) return rc;
+      // unfused sequence: the GEMM without the normalised output, then gn_finalize + gn_apply
       dp_gemm_desc g = *d;
       g.gn_out_bf16 = nullptr;
-      g.out_bf16 = e->buffers[braw];
-      g.stats = static_cast<float*>(e->buffers[bst]);
-      if (int rc = dp_op_gemm(e, &g)) return rc;
       dp_gn_desc n;
       std::memset(&n, 0, sizeof(n));
-      n.src0 = static_cast<const float*>(e->buffers[braw]);
-      n.src0_is_bf16 = 1;
-      n.stats0 = static_cast<const float*>(e->buffers[bst]);
+      if (late) {
+        n.src0 = d->out_f32;
+        n.stats0 = d->stats;
+      } else {   // engine-owned scratch: raw result in bf16 + partial statistics
+        int braw, bst;
+        const size_t rows = static_cast<size_t>(d->B) * hw;
+        if (int rc = dp_buffer_alloc(e, rows * d->N * 2, &braw)) return rc;
+        const size_t srows = hw >= 128 ? rows / 128 : static_cast<size_t>((d->B + 128 / hw - 1) / (128 / hw)) * (128 / hw);
+        if (int rc = dp_buffer_alloc(e, srows * d->N * 2 * sizeof(float), &bst)) return rc;
+        g.out_bf16 = e->buffers[braw];
+        g.stats = static_cast<float*>(e->buffers[bst]);
+        n.src0 = static_cast<const float*>(e->buffers[braw]);
+        n.src0_is_bf16 = 1;
+        n.stats0 = static_cast<const float*>(e->buffers[bst]);
+      }
+      if (int rc = dp_op_gemm(e, &g)) return rc;
       n.C0 = d->N;
       n.P0 = hw >= 128 ? hw / 128 : 1;
       n.gamma = d->gn_gamma; n.beta = d->gn_beta;
@@ -518,7 +528,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     bn = d->N;
   } else if (d->N <= 32 && !d->stats) {
     bn = 32;  // narrow output (the C->3|6 conv padded to 8 columns): 128x32 tiles waste 4x instead of 16x of the MMA
-  } else if (gn_fused && hw == 1024) {
+  } else if (gn_fused && hw == 1024 && !d->out_f32) {
     bn = 128;  // four resident accumulator stages need BN = 128
   } else if (d->N % 256 == 0 && kprobe > 512) {
     // (K <= 512: four to eight k-blocks per tile, the epilogue dominates and the 8-warp BN = 128 epilogue wins: measured
@@ -530,6 +540,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     if (static_cast<long long>(probe.m_tiles) * probe.n_tiles * probe.batch >= e->num_sms) bn = 256;
   }
   op.bn = bn;
+  if (gn_fused && bn == 128) p.acc_stages = 4;  // all 512 TMEM columns: the MMAs may run further ahead of the two-pass epilogue
   dp::gemm_fill_geometry(p, d->B, d->H, d->W, d->N, bn);
   const dp::TileBox tb = dp::gemm_tile_box(d->H, d->W);
   std::string err;

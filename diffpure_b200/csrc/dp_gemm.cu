@@ -843,11 +843,13 @@ void gemm_fill_geometry(GemmParams& p, int B, int H, int W, int N, int bn, int c
 
 int launch_gemm(const GemmParams& p, int bn, bool softmax, int num_sms, cudaStream_t stream, int cg) {
   if (p.gn_out != nullptr) {
-    // fused GroupNorm epilogue: bias / per-sample vector only, whole N tiles, groups inside a tile, accumulators of a
-    // work unit resident in TMEM
-    if (softmax || p.resid || p.rowscale || p.bias_along_m || p.silu || p.out_f32 || p.out_bf16 || p.stats ||
-        p.alpha != 1.0f || (bn != 128 && bn != 256) || p.N % bn || p.gn_cpg <= 0 || bn % p.gn_cpg || p.gn_cpg > 32 ||
-        p.tpg > p.acc_stages || p.acc_stages * bn > 512 ||
+    // fused GroupNorm epilogue: whole N tiles, groups inside a tile. Resident variant (no out_f32): bias / per-sample
+    // vector only, the work unit's accumulators stay in TMEM. Late variant (out_f32 given): + residual, alpha, raw bf16 copy
+    // and partial statistics, pass 2 re-reads the fp32 result.
+    const bool late = p.out_f32 != nullptr;
+    if (softmax || p.rowscale || p.bias_along_m || p.silu || (bn != 128 && bn != 256) || p.N % bn || p.gn_cpg <= 0 ||
+        bn % p.gn_cpg || p.gn_cpg > 32 || p.acc_stages * bn > 512 ||
+        (!late && (p.resid || p.out_bf16 || p.stats || p.alpha != 1.0f || p.tpg > p.acc_stages)) ||
         (p.upc == 2 && (cg != 2 || !p.xg_data || !p.xg_flag || !p.xg_epoch || p.stat_nseg != 1 || p.gn_xchg)))
       return static_cast<int>(cudaErrorInvalidValue);
     if (cg == 2) return bn == 256 ? launch_pair_t<256, E_GN>(p, num_sms, stream) : launch_pair_t<128, E_GN>(p, num_sms, stream);

@@ -19,6 +19,8 @@ class Act:
     W: int
     stats: Optional[Tensor]
     P: int  # partials per sample
+    pre: Optional[Tensor] = None    # bf16 act(GroupNorm(x)) already produced for the next block by the producer's epilogue
+    raw16: Optional[Tensor] = None  # bf16 copy of x written next to it (operand of the next block's 1x1 shortcut)
 
 
 def pack_conv3x3(w):

@@ -150,6 +150,38 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
     prog.gemm([act_seg(t2, temb_dim)], prog.const_bf16("temb.wall", w_all), n_all, temb_dim, 1, 1, B, n_all,
               bias=prog.const_f32("temb.ball", b_all), out_f32=temb_all)
 
+    # ---- the consumer of a block's output, seen from its producer ----------------------------------------
+    def consumer_gn(j, C):
+        """If the op after plan entry j-1 normalises the WHOLE incoming tensor (C channels) on its own -- a plain res-block
+        (no up / down resample in front of Conv_0, no channel concat), an attention block or the output GroupNorm -- return
+        what the producer's epilogue needs to emit that operand itself: dict(gamma, beta, groups, silu, raw16)."""
+        if not fuse_gn or tape is not None or j >= len(plan):
+            return None
+        kind, kw = plan[j]
+        if kind == "res" and kw["mode"] == 0 and kw["role"] in ("down", "mid") and kw["cin"] == C:
+            return dict(gamma=prog.const_f32(f"m{j}.gn0.w", P(j, "GroupNorm_0.weight")),
+                        beta=prog.const_f32(f"m{j}.gn0.b", P(j, "GroupNorm_0.bias")), groups=_groups(C), silu=1,
+                        raw16=kw["cin"] != kw["cout"])
+        if kind == "attn" and kw["c"] == C:
+            return dict(gamma=prog.const_f32(f"m{j}.gn.w", P(j, "GroupNorm_0.weight")),
+                        beta=prog.const_f32(f"m{j}.gn.b", P(j, "GroupNorm_0.bias")), groups=_groups(C), silu=0, raw16=False)
+        if kind == "gn_out" and kw["c"] == C:
+            return dict(gamma=prog.const_f32("out.gn.w", P(j, "weight")), beta=prog.const_f32("out.gn.b", P(j, "bias")),
+                        groups=_groups(C), silu=1, raw16=False)
+        return None
+
+    def gn_epilogue_args(out: Act, spec, name):
+        """gemm() keyword arguments that make the producer of `out` also write its consumer's normalised operand."""
+        if spec is None:
+            return {}
+        out.pre = prog.tensor(name + ".next_a0", B * out.H * out.W * out.C, "bf16")
+        kw = dict(gn_out=out.pre, gn_gamma=spec["gamma"], gn_beta=spec["beta"], gn_groups=spec["groups"], gn_eps=1e-6,
+                  gn_silu=spec["silu"])
+        if spec["raw16"]:
+            out.raw16 = prog.tensor(name + ".next_xb", B * out.H * out.W * out.C, "bf16")
+            kw["out_bf16"] = out.raw16
+        return kw
+
     # ---- blocks ---------------------------------------------------------------------------------------
     def resblock(i, kw, x0: Act, x1: Act = None):
         """ResnetBlockBigGANpp.forward, layerspp.py:242-274."""
@@ -159,14 +191,19 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
         Ho, Wo = (H * 2, W * 2) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
         shortcut = (cin != cout) or mode != 0
         name = f"m{i}"
-        a0 = prog.tensor(name + ".a0", B * Ho * Wo * cin, "bf16")
-        xb = prog.tensor(name + ".xb", B * Ho * Wo * cin, "bf16") if shortcut else None
-        prog.gn_apply(src0=x0.t, stats0=x0.stats, C0=x0.C, P0=x0.P,
-                      src1=x1.t if x1 else None, stats1=x1.stats if x1 else None, C1=x1.C if x1 else 0,
-                      P1=x1.P if x1 else 0,
-                      gamma=prog.const_f32(name + ".gn0.w", P(i, "GroupNorm_0.weight")),
-                      beta=prog.const_f32(name + ".gn0.b", P(i, "GroupNorm_0.bias")),
-                      B=B, H=H, W=W, groups=_groups(cin), eps=1e-6, silu=1, resample=mode, out_bf16=a0, raw_bf16=xb)
+        if x0.pre is not None and x1 is None and mode == 0:
+            # GroupNorm_0 + act of this block already came out of the producer's epilogue (and the raw bf16 copy with it)
+            a0, xb = x0.pre, x0.raw16
+            assert (xb is not None) == shortcut
+        else:
+            a0 = prog.tensor(name + ".a0", B * Ho * Wo * cin, "bf16")
+            xb = prog.tensor(name + ".xb", B * Ho * Wo * cin, "bf16") if shortcut else None
+            prog.gn_apply(src0=x0.t, stats0=x0.stats, C0=x0.C, P0=x0.P,
+                          src1=x1.t if x1 else None, stats1=x1.stats if x1 else None, C1=x1.C if x1 else 0,
+                          P1=x1.P if x1 else 0,
+                          gamma=prog.const_f32(name + ".gn0.w", P(i, "GroupNorm_0.weight")),
+                          beta=prog.const_f32(name + ".gn0.b", P(i, "GroupNorm_0.bias")),
+                          B=B, H=H, W=W, groups=_groups(cin), eps=1e-6, silu=1, resample=mode, out_bf16=a0, raw_bf16=xb)
         a1 = prog.tensor(name + ".a1", B * Ho * Wo * cout, "bf16")
         w0 = prog.const_bf16(name + ".w0", pack_conv3x3(P(i, "Conv_0.weight")))
         b0 = prog.const_f32(name + ".b0", P(i, "Conv_0.bias"))
@@ -189,17 +226,18 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
             prog.gn_apply(src0=h.t, stats0=h.stats, C0=cout, P0=h.P, gamma=gn1w, beta=gn1b,
                           B=B, H=Ho, W=Wo, groups=_groups(cout), eps=1e-6, silu=1, out_bf16=a1)
         out = new_act(prog, name + ".out", B, cout, Ho, Wo)
+        nxt = gn_epilogue_args(out, consumer_gn(i + 1, cout), name)   # the next block's GroupNorm_0 in this epilogue
         w1 = pack_conv3x3(P(i, "Conv_1.weight"))
         if shortcut:
             w = torch.cat([w1, pack_conv1x1(P(i, "Conv_2.weight"))], dim=1)
             bias = P(i, "Conv_1.bias") + P(i, "Conv_2.bias")
             prog.gemm([act_seg(a1, cout, taps=9), act_seg(xb, cin)], prog.const_bf16(name + ".w1", w), cout,
                       9 * cout + cin, B, Ho, Wo, cout, bias=prog.const_f32(name + ".b1", bias), alpha=INV_SQRT2,
-                      out_f32=out.t, stats=out.stats)
+                      out_f32=out.t, stats=out.stats, **nxt)
         else:
             prog.gemm([act_seg(a1, cout, taps=9)], prog.const_bf16(name + ".w1", w1), cout, 9 * cout, B, Ho, Wo, cout,
                       bias=prog.const_f32(name + ".b1", P(i, "Conv_1.bias")), resid=x0.t, alpha=INV_SQRT2,
-                      out_f32=out.t, stats=out.stats)
+                      out_f32=out.t, stats=out.stats, **nxt)
         if tape is not None:
             tape.append(dict(kind="res", i=i, kw=kw, x0=x0, x1=x1, h=h, out=out, shortcut=shortcut, Ho=Ho, Wo=Wo))
         return out
@@ -209,11 +247,14 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
         C, H, W = x.C, x.H, x.W
         T = H * W
         name = f"m{i}"
-        hn = prog.tensor(name + ".hn", B * T * C, "bf16")
-        prog.gn_apply(src0=x.t, stats0=x.stats, C0=C, P0=x.P,
-                      gamma=prog.const_f32(name + ".gn.w", P(i, "GroupNorm_0.weight")),
-                      beta=prog.const_f32(name + ".gn.b", P(i, "GroupNorm_0.bias")),
-                      B=B, H=H, W=W, groups=_groups(C), eps=1e-6, silu=0, out_bf16=hn)
+        if x.pre is not None:
+            hn = x.pre                    # GroupNorm_0 of this block came out of the producer's epilogue
+        else:
+            hn = prog.tensor(name + ".hn", B * T * C, "bf16")
+            prog.gn_apply(src0=x.t, stats0=x.stats, C0=C, P0=x.P,
+                          gamma=prog.const_f32(name + ".gn.w", P(i, "GroupNorm_0.weight")),
+                          beta=prog.const_f32(name + ".gn.b", P(i, "GroupNorm_0.bias")),
+                          B=B, H=H, W=W, groups=_groups(C), eps=1e-6, silu=0, out_bf16=hn)
         wq, wk, wv = (P(i, f"NIN_{j}.W").t().contiguous() for j in range(3))   # NIN: y = x.W + b, W is [in, out]
         bq, bk, bv = (P(i, f"NIN_{j}.b") for j in range(3))
         o = prog.tensor(name + ".o", B * T * C, "bf16")
@@ -242,9 +283,10 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
             prog.gemm([act_seg(pm, T)], vt, B * C, T, 1, 1, T, C, batch=B, a_batch_rows=T, b_batch_rows=C,
                       out_batch_stride=T * C, rowscale=rs, out_bf16=o, ldc=C)
         out = new_act(prog, name + ".out", B, C, H, W)
+        nxt = gn_epilogue_args(out, consumer_gn(i + 1, C), name)
         prog.gemm([act_seg(o, C)], prog.const_bf16(name + ".w3", P(i, "NIN_3.W").t().contiguous()), C, C, B, H, W, C,
                   bias=prog.const_f32(name + ".b3", P(i, "NIN_3.b")), resid=x.t, alpha=INV_SQRT2, out_f32=out.t,
-                  stats=out.stats)
+                  stats=out.stats, **nxt)
         if tape is not None:
             rec = dict(kind="attn", i=i, x=x, out=out, T=T, C=C, scale=C ** -0.5)
             if T <= 64:
@@ -295,10 +337,13 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
         tape.insert(0, dict(kind="conv_in", out=h0))
         prog.meta.update(model="ncsnpp", out_channels=cfg.num_channels, cond="999*t")
         return prog
-    a = prog.tensor("out.a", B * S * S * C, "bf16")
-    prog.gn_apply(src0=h.t, stats0=h.stats, C0=C, P0=h.P, gamma=prog.const_f32("out.gn.w", P(idx, "weight")),
-                  beta=prog.const_f32("out.gn.b", P(idx, "bias")), B=B, H=S, W=S, groups=_groups(C), eps=1e-6,
-                  silu=1, out_bf16=a)
+    if h.pre is not None:
+        a = h.pre                         # the output GroupNorm + act came out of the last block's epilogue
+    else:
+        a = prog.tensor("out.a", B * S * S * C, "bf16")
+        prog.gn_apply(src0=h.t, stats0=h.stats, C0=C, P0=h.P, gamma=prog.const_f32("out.gn.w", P(idx, "weight")),
+                      beta=prog.const_f32("out.gn.b", P(idx, "bias")), B=B, H=S, W=S, groups=_groups(C), eps=1e-6,
+                      silu=1, out_bf16=a)
     idx += 1
     prog.conv_out_gemm("out", a, P(idx, "weight"), P(idx, "bias"), B, S, S, C, cfg.num_channels)
     idx += 1

@@ -106,11 +106,13 @@ typedef struct {
   float* out_f32; void* out_bf16; long long ldc;
   float* stats;          /* [ceil(M/seg)][N][2] partial (sum, sumsq), seg = min(H*W,128); or NULL */
   int softmax; float softmax_scale; float* rowsum_out;
-  /* Fused GroupNorm(+SiLU) of the result (score_sde/models/layerspp.py:259-266: Conv_0 + Dense_0(act(temb)) -> GroupNorm_1
-   * -> act, read only by Conv_1): gn_out_bf16 = act(GN(acc + bias + rowvec)) [same layout as out_bf16]. With gn_out_bf16
-   * set, out_f32 / out_bf16 / stats must be NULL (the raw result is never materialised); resid / rowscale / alpha / silu
-   * are not combined with it. Shapes the tcgen05 epilogue cannot keep resident in TMEM (a sample spanning more than 4
-   * CTA-pair tiles) fall back inside the engine to GEMM + gn_finalize + gn_apply with engine-owned scratch. */
+  /* Fused GroupNorm(+SiLU) of the result: gn_out_bf16 = act(GN(v)) [same layout as out_bf16], v = the epilogue's result.
+   *  - without out_f32 (score_sde/models/layerspp.py:259-266: Conv_0 + Dense_0(act(temb)) -> GroupNorm_1 -> act, read only
+   *    by Conv_1): v = acc + bias + rowvec is never materialised (out_bf16 / stats / resid must be NULL, alpha 1): the
+   *    sample's accumulators stay resident in TMEM between the statistics pass and the normalising pass;
+   *  - with out_f32 (+ stats, optionally resid / alpha / a raw bf16 copy in out_bf16; layerspp.py:245-251,78: Conv_1 / NIN_3
+   *    whose result is the next block's GroupNorm_0 input): v is written as usual and the normalising pass re-reads it.
+   * Shapes whose sample does not fit the tile / TMEM scheme fall back inside the engine to GEMM + gn_finalize + gn_apply. */
   void* gn_out_bf16; const float* gn_gamma; const float* gn_beta; int gn_groups; float gn_eps; int gn_silu;
 } dp_gemm_desc;
 

@@ -137,7 +137,7 @@ class Interp:
                 D = D + torch.as_strided(rb, (M, N), (ldc, 1), ro + obs)
             D = D * alpha
             if gn_out is not None:        # fused GroupNorm(+SiLU) epilogue: statistics of the fp32 result per sample
-                assert batch == 1 and out_f32 is None and out_bf16 is None and stats is None
+                assert batch == 1 and (out_f32 is not None or (out_bf16 is None and stats is None and resid is None))
                 x = D.reshape(B, H * W, gn_groups, N // gn_groups)
                 mean = x.double().mean((1, 3), keepdim=True)
                 var = (x.double() * x.double()).mean((1, 3), keepdim=True) - mean * mean

@@ -57,6 +57,7 @@ struct ConvCase {
   float alpha;
   int cg;             // 0/1 = one CTA per tile, 2 = CTA pair (cta_group::2)
   int gn;             // 1 = fused GroupNorm + SiLU epilogue (bf16 output only; the sample's accumulators stay in TMEM)
+                      // 2 = "late" variant: fp32 result (+ residual, alpha, statistics, raw bf16 copy) AND its GroupNorm + SiLU
 };
 
 static int num_sms = 148;
@@ -102,12 +103,15 @@ static void run_conv(const ConvCase& cs) {
   for (auto& v : beta) v = 0.3f * frand();
   float* d_gamma = dev(gamma);
   float* d_beta = dev(beta);
+  __nv_bfloat16* d_gn = nullptr;
+  CK(cudaMalloc(&d_gn, (size_t)M * N * 2));
   if (cs.gn) {
-    p.gn_out = d_outb;
+    p.gn_out = cs.gn == 2 ? d_gn : d_outb;
     p.gn_gamma = d_gamma; p.gn_beta = d_beta;
     p.gn_cpg = N / groups; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
     const bool super_pair = strstr(cs.name, "super-pair") != nullptr;
     if (H * W == 1024 && !super_pair) { p.tpg = 4; p.acc_stages = 4; }  // the sample's four tiles resident in one pair
+    if (cs.bn == 128) p.acc_stages = 4;
     if (H * W == 1024 && super_pair) {  // two CTA pairs per sample, exchange through global memory
       p.tpg = 2; p.upc = 2; p.acc_stages = 4;
       static void* xg = nullptr;
@@ -162,12 +166,12 @@ static void run_conv(const ConvCase& cs) {
   p.alpha = cs.alpha;
   p.silu = cs.silu;
   // pair kernels exist for the lowerings' epilogues only: a bf16 case writes bf16 alone there
-  const bool f32_out = !cs.gn && !((cg == 2 || !strncmp(cs.name, "bf16only", 8)) && cs.out_bf16);
+  const bool f32_out = cs.gn == 2 || (!cs.gn && !((cg == 2 || !strncmp(cs.name, "bf16only", 8)) && cs.out_bf16));
   p.out_f32 = f32_out ? d_out : nullptr;
-  p.out_bf16 = (cs.out_bf16 && !cs.gn) ? d_outb : nullptr;
+  p.out_bf16 = (cs.out_bf16 && cs.gn != 1) ? d_outb : nullptr;
   p.ldc = N;
   p.out_batch_stride = 0;
-  p.stats = (cs.stats && !cs.gn) ? d_stats : nullptr;
+  p.stats = (cs.stats && cs.gn != 1) ? d_stats : nullptr;
 
   int e = dp::launch_gemm(p, cs.bn, false, num_sms, 0, cg);
   cudaError_t se = cudaDeviceSynchronize();
@@ -177,9 +181,10 @@ static void run_conv(const ConvCase& cs) {
     exit(3);
   }
   std::vector<float> out((size_t)M * N), stats((size_t)nsegs_total * N * 2);
-  std::vector<__nv_bfloat16> outb((size_t)M * N);
+  std::vector<__nv_bfloat16> outb((size_t)M * N), gnb((size_t)M * N);
   CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(outb.data(), d_outb, outb.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(gnb.data(), d_gn, gnb.size() * 2, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(stats.data(), d_stats, stats.size() * 4, cudaMemcpyDeviceToHost));
 
   // host reference
@@ -215,11 +220,12 @@ static void run_conv(const ConvCase& cs) {
           if (cs.silu) v = v / (1.f + expf(-v));
           if (cs.resid) v += resid[row * N + n];
           v *= cs.alpha;
-          if (cs.gn) { vall[row * N + n] = v; continue; }
+          if (cs.gn) vall[row * N + n] = v;
+          if (cs.gn == 1) continue;
           const double d = f32_out ? fabs((double)v - out[row * N + n]) : 0.0;
           if (d > maxerr) maxerr = d;
           if (fabs(v) > maxref) maxref = fabs(v);
-          if (cs.out_bf16) {
+          if (cs.out_bf16 && cs.gn != 2) {
             const double db = fabs((double)v - __bfloat162float(outb[row * N + n]));
             if (db > maxerr_b) maxerr_b = db;
           }
@@ -246,13 +252,14 @@ static void run_conv(const ConvCase& cs) {
             const size_t i = ((size_t)b * hw + px) * N + n_;
             double y = (vall[i] - mean) * rstd * gamma[n_] + beta[n_];
             y = y / (1.0 + exp(-y));
-            maxerr_b = fmax(maxerr_b, fabs(y - __bfloat162float(outb[i])));
+            maxerr_b = fmax(maxerr_b, fabs(y - __bfloat162float(cs.gn == 2 ? gnb[i] : outb[i])));
+            if (cs.gn == 2 && cs.out_bf16) maxerr_b = fmax(maxerr_b, fabs((double)vall[i] - __bfloat162float(outb[i])));
             maxref = fmax(maxref, fabs(y));
           }
       }
   }
   double maxs = 0, maxsref = 0;
-  if (cs.stats && !cs.gn) {
+  if (cs.stats && cs.gn != 1) {
     const size_t nvalid = (size_t)((M + seg_rows - 1) / seg_rows) * N * 2;
     for (size_t i = 0; i < nvalid; ++i) {
       maxs = fmax(maxs, fabs(rs[i] - stats[i]));
@@ -260,12 +267,12 @@ static void run_conv(const ConvCase& cs) {
     }
   }
   const bool ok = maxerr <= 2e-3 * fmax(1.0, maxref) && (!(cs.out_bf16 || cs.gn) || maxerr_b <= 1e-2 * fmax(1.0, maxref)) &&
-                  (!cs.stats || cs.gn || maxs <= 1e-3 * fmax(1.0, maxsref));
+                  (!cs.stats || cs.gn == 1 || maxs <= 1e-3 * fmax(1.0, maxsref));
   printf("[%s] %s  max|err|=%.3e (max|ref|=%.3f) bf16out err=%.3e stats err=%.3e (ref %.2f)\n", cs.name,
          ok ? "OK  " : "FAIL", maxerr, maxref, maxerr_b, maxs, maxsref);
   if (!ok) failures++;
   cudaFree(d_a0); cudaFree(d_a1); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_rowvec); cudaFree(d_resid);
-  cudaFree(d_out); cudaFree(d_outb); cudaFree(d_stats); cudaFree(d_gamma); cudaFree(d_beta);
+  cudaFree(d_out); cudaFree(d_outb); cudaFree(d_stats); cudaFree(d_gamma); cudaFree(d_beta); cudaFree(d_gn);
 }
 
 // Batched attention-style GEMMs: S = softmax-numerator(Q K^T) then O = P V^T-layout.
@@ -465,6 +472,14 @@ int main(int argc, char** argv) {
       {"gn pair 8x8 256 bn128",                                   8, 8,  8,  256, 9, 0, 256, 128, 1, true, true, false,false,false,true, 1.f, 2, 1},
       {"gn single 4x4 256 bn256 (ragged)",                        11, 4, 4,  256, 9, 0, 256, 256, 1, true, true, false,false,false,true, 1.f, 1, 1},
       {"gn pair 4x4 256 bn128 no rowvec",                         32, 4, 4,  256, 9, 0, 256, 128, 1, true, false,false,false,false,true, 1.f, 2, 1},
+      // "late" variant: fp32 result with residual / alpha / statistics AND the next block's GroupNorm + SiLU operand
+      {"gn-late pair 32x32 128->128 resid",                       3, 32, 32, 128, 9, 0, 128, 128, 1, true, false,true, false,true, false, 0.70710678f, 2, 2},
+      {"gn-late pair 32x32 +1x1 raw16",                           2, 32, 32, 128, 9, 256, 128, 128, 1, true, false,false,false,true, true, 0.70710678f, 2, 2},
+      {"gn-late pair 16x16 256->256 bn256 resid",                 5, 16, 16, 256, 9, 0, 256, 256, 1, true, false,true, false,true, false, 0.70710678f, 2, 2},
+      {"gn-late pair 16x16 1x1 (NIN_3) resid",                    6, 16, 16, 256, 1, 0, 256, 128, 1, true, false,true, false,true, false, 0.70710678f, 2, 2},
+      {"gn-late single 8x8 256 bn128 resid (ragged)",             5, 8,  8,  256, 9, 0, 256, 128, 1, true, false,true, false,true, false, 0.70710678f, 1, 2},
+      {"gn-late pair 4x4 256 bn128 resid",                        32, 4, 4,  256, 9, 0, 256, 128, 1, true, false,true, false,true, false, 0.70710678f, 2, 2},
+      {"gn-late single 4x4 256 bn256 resid (ragged)",             11, 4, 4,  256, 9, 0, 256, 256, 1, true, false,true, false,true, false, 0.70710678f, 1, 2},
   };
   const int ncases = sizeof(cases) / sizeof(cases[0]);
   for (int i = 0; i < ncases; ++i) {
