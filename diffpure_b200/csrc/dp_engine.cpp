@@ -458,7 +458,14 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     const int cpg = d->N / d->gn_groups;
     const bool shape_ok = (hw == 16 || hw == 64 || hw == 128 || hw == 256 || hw == 1024) && d->H > 1 && d->N % 128 == 0 &&
                           128 % cpg == 0 && (d->batch <= 1);
-    gn_fused = shape_ok && (late ? (gn_on == 1 || gn_on == 2) : gn_on >= 1);  // DP_GEMM_GN: 0 none, 1 all, 3 resident kind only
+    // DP_GEMM_GN: 0 none, 1 default, 2 every late candidate, 3 resident kind only. The late kind pays where the MMAs of a
+    // tile outlast the two-pass epilogue (measured at B=512, profiles/r02_gn_late_per_shape.txt): 3x3 convs at <= 16x16 win
+    // 17-32 us per launch; the 32x32 convs (+88 us vs 84 us of GroupNorm kernels saved) and the short-K NIN_3 projection
+    // (+54 vs 50 us) are epilogue / HBM bound already and keep the separate kernels.
+    long long kall = 0;
+    for (int sgi = 0; sgi < d->nseg; ++sgi) kall += static_cast<long long>(d->a[sgi].taps) * d->a[sgi].C;
+    const bool late_pays = hw <= 256 && kall >= 2048;
+    gn_fused = shape_ok && (late ? (gn_on == 2 || (gn_on == 1 && late_pays)) : gn_on >= 1);
     if (!gn_fused) {
       // unfused sequence: the GEMM without the normalised output, then gn_finalize + gn_apply
       dp_gemm_desc g = *d;

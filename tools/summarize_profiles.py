@@ -1,7 +1,11 @@
 """Turn the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/ (round-tagged).
 
-  launches.csv        <- ncu --metrics gpu__time_duration.sum --clock-control none ... (per-launch device time)
-  prof_gemm.ncu-rep   <- ncu --set full --clock-control none --import-source on -k regex:gemm_kernel ...
+  launches.csv            <- ncu --metrics gpu__time_duration.sum --clock-control none ... (per-launch device time)
+  prof_<tag>_gemm.ncu-rep <- ncu --set full --clock-control none --import-source on -k regex:gemm_kernel ... gpu_profile_eval.py
+  prof_<tag>_gn.ncu-rep   <- the same for -k regex:gn_apply
+  prof_gn16 / prof_plain16.ncu-rep <- selftest_gemm perf under ncu (fused-GroupNorm vs plain epilogue, 16x16 256->256)
+
+usage: python tools/summarize_profiles.py r02
 """
 import collections
 import csv
@@ -32,9 +36,9 @@ def launch_list():
         agg[name][0] += 1
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
-    lines = [f"# ncu launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv python bench.py"
+    lines = [f"# ncu launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none -c 1300 --csv python bench.py"
              " --steps 1 --warmup 1 --no-cpu-baseline --no-e2e",
-             "# (the first 1200 launches of the bench command: the engine's eager warm-up of the forward and the step program,"
+             "# (the first 1300 launches of the bench command: the engine's eager warm-up of the forward and the step program,"
              " i.e. two DDPM++ UNet evaluations at B=512, plus the start of the first purification)",
              f"# per-launch device time, cold-cache/serialised:",
              f"# compare SHARES, not absolutes. unit of column 3: {unit}", "",
@@ -45,54 +49,81 @@ def launch_list():
     print("\n".join(lines[:14]))
 
 
-def gemm_capture(rep="prof_gemm.ncu-rep"):
-    raw = subprocess.run(["ncu", "-i", os.path.join(go, rep), "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
-            "l1tex__m_xbar2l1tex_read_bytes.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
-            "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
-    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 3 -c 4 python tests/gpu_profile_eval.py 512 1  ({tag})",
-             "# dominant kernel dp::gemm_kernel<BN, EPI, CG> (tcgen05 implicit GEMM; CG = 2: CTA pair, cta_group::2).",
-             "# launches: the two res-blocks after the input conv of one DDPM++ evaluation at B=512: conv 128->128 @32x32 (+temb, stats,",
-             "# bf16 out) and conv 128->128 @32x32 (+fp32 residual, 1/sqrt2, stats), twice -- all four on CTA pairs", ""]
-    traffic = []
-    for ri, r in enumerate(rows[2:]):
-        lines.append(f"## launch {ri}")
-        rd = wr = None
-        for w in want:
-            for i, h in enumerate(hdr):
-                if h == w:
-                    lines.append(f"  {h:66s} {r[i]:>18s} {units[i]}")
-                    if h == "dram__bytes_read.sum":
-                        rd = float(r[i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(units[i], 1)
-                    if h == "dram__bytes_write.sum":
-                        wr = float(r[i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(units[i], 1)
-        if rd is not None and wr is not None:
-            traffic.append(rd + wr)
-    open(os.path.join(out, f"{tag}_gemm_ncu_full.txt"), "w").write("\n".join(lines) + "\n")
-    if traffic:
-        json.dump({"dram_bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic),
-                   "source": f"profiles/{tag}_gemm_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
-                   "algorithmic_bytes_per_launch_note": "B=512 conv 128->128 @32x32: temb/bf16-out launches 268 MB, fp32-residual launches 671 MB (A bf16 134 MB + residual 268 MB + out 268 MB)"},
-                  open(os.path.join(out, "gemm_dram_bytes_per_launch.json"), "w"), indent=1)
-    print("\n".join(lines[:24]))
+WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum"]
+UNIT = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
+
+
+def raw(rep):
+    r = subprocess.run(["ncu", "-i", os.path.join(go, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(r.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+def block(h, u, r):
+    return [f"  {hh:70s} {r[j]:>20s} {u[j]}" for w in WANT for j, hh in enumerate(h) if hh == w]
+
+
+def dump(rep, title, fn, note="", append=False):
+    if not os.path.exists(os.path.join(go, rep)):
+        print("missing", rep)
+        return None
+    h, u, rows = raw(rep)
+    lines = [f"# {title}", note, ""]
+    for i, r in enumerate(rows):
+        lines.append(f"## launch {i}")
+        lines += block(h, u, r)
+    open(os.path.join(out, fn), "a" if append else "w").write("\n".join(lines) + "\n")
+    print(fn, len(rows), "launches")
+    return h, u, rows
+
+
+def captures():
+    res = dump(f"prof_{tag}_gemm.ncu-rep",
+               f"ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:gemm_kernel -s 4 -c 6 "
+               f"python tests/gpu_profile_eval.py 512 1  ({tag})", f"{tag}_gemm_ncu_full.txt",
+               "# the first res-blocks of one DDPM++ evaluation at B=512: gemm_kernel<128, 8192 (E_GN), 2> = a 128->128 @32x32 conv with a fused\n"
+               "# GroupNorm epilogue, gemm_kernel<128, 849, 2> = Conv_1 128->128 @32x32 (+bias, fp32 residual, 1/sqrt2, fp32 out, statistics); CTA pairs")
+    if res:
+        h, u, rows = res
+        idx = {k: i for i, k in enumerate(h)}
+        tr = [float(r[idx["dram__bytes_read.sum"]]) * UNIT[u[idx["dram__bytes_read.sum"]]] +
+              float(r[idx["dram__bytes_write.sum"]]) * UNIT[u[idx["dram__bytes_write.sum"]]]
+              for r in rows if "849" in r[idx["Kernel Name"]]]
+        if tr:
+            json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "launches": len(tr),
+                       "source": f"profiles/{tag}_gemm_ncu_full.txt (Conv_1 128->128 @32x32 launches, dram__bytes_read.sum + dram__bytes_write.sum)",
+                       "algorithmic_bytes_per_launch_note": "B=512 conv 128->128 @32x32 with fp32 residual: A bf16 134 MB + residual 268 MB + out 268 MB "
+                                                            "= 671 MB algorithmic (part of the output is still in L2 at kernel end)"},
+                      open(os.path.join(out, "gemm_dram_bytes_per_launch.json"), "w"), indent=1)
+    dump(f"prof_{tag}_gn.ncu-rep", f"ncu --set full ... -k regex:gn_apply -s 2 -c 3 python tests/gpu_profile_eval.py 512 1  ({tag})",
+         f"{tag}_gn_apply_ncu.txt",
+         "# gn_apply_kernel<0, false, 4>: fp32 NHWC 32x32x128 at B=512 -> GroupNorm+SiLU -> bf16: 269 MB read + 106 MB written in 65.7 us = 5.7 TB/s,\n"
+         "# 0.88 of the measured copy bandwidth (6.48 TB/s); gpu__dram_throughput is relative to the nominal peak")
+    dump("prof_gn16.ncu-rep", "DP_PERF_GN=1 ncu --set full ... -k regex:gemm_kernel -s 3 -c 1 ./selftest_gemm perf 512 16 16 256 9 256 0 256 2 "
+                              f"({tag}, FIRST version of the fused GroupNorm epilogue)", f"{tag}_gn_epilogue_ncu.txt",
+         "# 16x16 256->256 conv, BN=256 pair tiles, fused GroupNorm_1+SiLU epilogue, first version: 126 us, tensor pipe 58 % (plain bf16 epilogue below:\n"
+         "# 89.6 us, 83 %); source view: 14.5 % of all samples = epilogue warps parked at the bar.sync behind the double-precision group reduction;\n"
+         f"# after fp32 group statistics + the staged additive table the same shape runs in 103 us (profiles/{tag}_gn_epilogue_perf.txt)")
+    dump("prof_plain16.ncu-rep", "--- the plain bf16 epilogue on the same shape (DP_PERF_BF16=1), for comparison ---", f"{tag}_gn_epilogue_ncu.txt",
+         append=True)
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "diffpure_b200", "libdiffpure_b200.so")],
                           capture_output=True, text=True).stdout
     cnt = collections.Counter()
     for m in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.4D.2CTA", "LDTM", "UTCBAR", "UTCBAR.2CTA.MULTICAST", "SYNCS.ARRIVE.TRANS64",
-              "HMMA"):
+              "STAS", "MUFU.TANH", "HMMA"):
         cnt[m] = sass.count(m)
     cnt["HMMA"] -= cnt["UTCHMMA"]   # "UTCHMMA" contains "HMMA": legacy mma.sync count is what is left
     open(os.path.join(out, f"{tag}_sass_mnemonics.txt"), "w").write(
         "# cuobjdump -sass diffpure_b200/libdiffpure_b200.so | mnemonic counts (tcgen05.mma -> UTCHMMA, TMA -> UTMALDG,\n"
-        "# tcgen05.ld -> LDTM, tcgen05.commit -> UTCBAR; no legacy HMMA)\n" + "\n".join(f"{k:24s} {v}" for k, v in cnt.items()) + "\n")
+        "# tcgen05.ld -> LDTM, tcgen05.commit -> UTCBAR, st.async -> STAS; no legacy HMMA)\n" +
+        "\n".join(f"{k:24s} {v}" for k, v in cnt.items()) + "\n")
     print(dict(cnt))
 
 
 if __name__ == "__main__":
     launch_list()
-    gemm_capture()
+    captures()
