@@ -692,6 +692,32 @@ int launch_final_post(const float* x_nhwc, float* out_nchw, int B, int C, int H,
   return static_cast<int>(cudaGetLastError());
 }
 
+// state x (fp32 NHWC, 3 channels) -> bf16 NHWC zero-padded to Cpad channels: the A operand of the input conv on the tensor
+// cores (K = 9 * 64 of which 27 columns are non-zero: 21x redundant MMAs that still beat the SIMT conv 6x at 256x256)
+__global__ void __launch_bounds__(256) pad_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                     long long npix, int Cpad) {
+  pdl_entry();
+  const int vpp = Cpad / 8;                                   // 16-byte vectors per pixel
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * vpp) return;
+  const long long pix = i / vpp;
+  const int v = static_cast<int>(i - pix * vpp);
+  uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+  if (v == 0) {
+    const float a = x[pix * 3], b = x[pix * 3 + 1], c = x[pix * 3 + 2];
+    pk.x = pack_bf16x2(a, b);
+    pk.y = pack_bf16x2(c, 0.f);
+  }
+  *reinterpret_cast<uint4*>(out + pix * Cpad + v * 8) = pk;
+}
+
+int launch_pad_in(const float* x_nhwc3, __nv_bfloat16* out, long long npix, int Cpad, cudaStream_t s) {
+  if (Cpad % 8) return static_cast<int>(cudaErrorInvalidValue);
+  const long long n = npix * (Cpad / 8);
+  (void)launch_k(pad_in_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, s, 1, x_nhwc3, out, npix, Cpad);
+  return static_cast<int>(cudaGetLastError());
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
   pdl_entry();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

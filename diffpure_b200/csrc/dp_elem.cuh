@@ -80,6 +80,8 @@ int launch_init_state(const float* x0_nchw, const float* noise_nchw, float* x_nh
                       float sx, float se, unsigned long long seed, unsigned long long sample_offset,
                       cudaStream_t s);
 int launch_nhwc_to_nchw(const float* x_nhwc, float* out_nchw, int B, int C, int HW, cudaStream_t s);
+// engine state (fp32 NHWC, 3 channels) -> bf16 NHWC zero-padded to Cpad channels (A operand of the tensor-core input conv)
+int launch_pad_in(const float* x_nhwc3, __nv_bfloat16* out, long long npix, int Cpad, cudaStream_t s);
 // Fused pre / post steps of the caller (eval_sde_adv.py:73-89, utils.py:144-153): bilinear resize (align_corners = False)
 // + [0,1] -> [-1,1] in front of the forward diffusion; resize + [-1,1] -> [0,1] + classifier normalisation behind the loop.
 struct PostParams {

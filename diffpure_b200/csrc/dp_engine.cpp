@@ -20,7 +20,7 @@ namespace {
 std::string g_create_error;
 
 enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX, OP_UPDATE,
-              OP_GN_BWD, OP_SOFTMAX_BWD, OP_TRANSPOSE, OP_ATTN_SMALL_BWD, OP_GRAD_IN, OP_GN_FINALIZE };
+              OP_GN_BWD, OP_SOFTMAX_BWD, OP_TRANSPOSE, OP_ATTN_SMALL_BWD, OP_GRAD_IN, OP_GN_FINALIZE, OP_PAD_IN };
 
 struct StatsReduce {
   const float* in;
@@ -55,6 +55,7 @@ struct Op {
   dp::TransposeParams tr;
   dp::AttnSmallBwdParams attnb;
   dp_grad_in_desc gin;
+  dp_pad_in_desc pin;
 };
 
 }  // namespace
@@ -217,6 +218,10 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       break;
     case OP_ATTN_SMALL_BWD:
       rc = dp::launch_attn_small_bwd(op.attnb, s);
+      break;
+    case OP_PAD_IN:
+      rc = dp::launch_pad_in(e->x_state, static_cast<__nv_bfloat16*>(op.pin.out_bf16),
+                             static_cast<long long>(op.pin.B) * op.pin.H * op.pin.W, op.pin.Cpad, s);
       break;
     case OP_GRAD_IN:
       rc = dp::launch_grad_in(e->g_in, static_cast<__nv_bfloat16*>(op.gin.out_bf16), op.gin.B, op.gin.C,
@@ -805,6 +810,17 @@ int dp_op_attn_small_bwd(dp_engine* e, const dp_attn_small_bwd_desc* d) {
   op.attnb.go = static_cast<const __nv_bfloat16*>(d->go_bf16);
   op.attnb.out = static_cast<__nv_bfloat16*>(d->out_bf16);
   op.attnb.B = d->B; op.attnb.T = d->T; op.attnb.heads = d->heads; op.attnb.d = d->d; op.attnb.scale = d->scale;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
+int dp_op_pad_in(dp_engine* e, const dp_pad_in_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->Cpad < 8 || d->Cpad % 8 || !d->out_bf16) return fail(e, DP_ERR_INVALID, "pad_in: Cpad must be a multiple of 8");
+  Op op;
+  op.kind = OP_PAD_IN;
+  op.pin = *d;
   e->ops.push_back(op);
   return DP_OK;
 }

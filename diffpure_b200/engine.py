@@ -239,6 +239,9 @@ class Engine:
                 d = _lib.AttnSmallBwdDesc(self._p(a["qkv"]), self._p(a["go"]), self._p(a["out"]), a["B"], a["T"],
                                           a["heads"], a["d"], a["scale"])
                 self._check(L.dp_op_attn_small_bwd(self.h, C.byref(d)), "dp_op_attn_small_bwd")
+            elif op.kind == "pad_in":
+                d = _lib.PadInDesc(self._p(a["out"]), a["B"], a["H"], a["W"], a["Cpad"])
+                self._check(L.dp_op_pad_in(self.h, C.byref(d)), "dp_op_pad_in")
             elif op.kind == "grad_in":
                 d = _lib.GradInDesc(self._p(a["out"]), a["B"], a["H"], a["W"], a["C"], a["Cpad"])
                 self._check(L.dp_op_grad_in(self.h, C.byref(d)), "dp_op_grad_in")
@@ -344,7 +347,7 @@ class Engine:
         return out
 
     OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "attn_small",
-                "softmax_rows", "update", "gn_bwd", "softmax_bwd", "transpose", "attn_small_bwd", "grad_in", "gn_finalize")
+                "softmax_rows", "update", "gn_bwd", "softmax_bwd", "transpose", "attn_small_bwd", "grad_in", "gn_finalize", "pad_in")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

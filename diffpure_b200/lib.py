@@ -98,6 +98,10 @@ class GradInDesc(C.Structure):
                 ("Cpad", C.c_int)]
 
 
+class PadInDesc(C.Structure):
+    _fields_ = [("out_bf16", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cpad", C.c_int)]
+
+
 class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
@@ -133,6 +137,7 @@ SYMBOLS = {
     "dp_op_transpose": (C.c_int, [C.c_void_p, C.POINTER(TransposeDesc)]),
     "dp_op_attn_small_bwd": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallBwdDesc)]),
     "dp_op_grad_in": (C.c_int, [C.c_void_p, C.POINTER(GradInDesc)]),
+    "dp_op_pad_in": (C.c_int, [C.c_void_p, C.POINTER(PadInDesc)]),
     "dp_unet_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dp_program_size": (C.c_int, [C.c_void_p]),
     "dp_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),

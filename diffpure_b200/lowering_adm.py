@@ -226,8 +226,7 @@ def lower(cfg, sd, B, h_bf16=True):
     # ---- UNetModel.forward, unet.py:642-671 ---------------------------------------------------------------
     ch0 = inp[0][0][1]["cout"]
     h = new_act(prog, "conv_in.out", B, ch0, S, S)
-    prog.conv_in(prog.const_f32("conv_in.w", pack_conv_in(P("input_blocks.0.0.weight"))),
-                 prog.const_f32("conv_in.b", P("input_blocks.0.0.bias")), h.t, h.stats, B, S, S, ch0)
+    prog.conv_in_gemm("conv_in", P("input_blocks.0.0.weight"), P("input_blocks.0.0.bias"), h.t, h.stats, B, S, S, ch0)
     hs = [h]
     for i, layers in enumerate(inp[1:], start=1):
         h = run(f"input_blocks.{i}.", layers, h)

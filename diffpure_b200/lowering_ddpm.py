@@ -202,8 +202,7 @@ def lower(cfg, sd, B, h_bf16=True):
 
     # ---- Model.forward, unet_ddpm.py:305-345 -------------------------------------------------------------
     h0 = new_act(prog, "conv_in.out", B, ch, S, S)
-    prog.conv_in(prog.const_f32("conv_in.w", pack_conv_in(P("conv_in.weight"))),
-                 prog.const_f32("conv_in.b", P("conv_in.bias")), h0.t, h0.stats, B, S, S, ch)
+    prog.conv_in_gemm("conv_in", P("conv_in.weight"), P("conv_in.bias"), h0.t, h0.stats, B, S, S, ch)
     hs = [h0]
     res = S
     for lvl in range(nres):

@@ -299,8 +299,7 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
     # ---- walk the module list exactly as NCSNpp.forward does (ncsnpp.py:263-381) ----------------------
     idx = 2
     h0 = new_act(prog, "conv_in.out", B, nf, S, S)
-    prog.conv_in(prog.const_f32("conv_in.w", pack_conv_in(P(2, "weight"))), prog.const_f32("conv_in.b", P(2, "bias")),
-                 h0.t, h0.stats, B, S, S, nf)
+    prog.conv_in_gemm("conv_in", P(2, "weight"), P(2, "bias"), h0.t, h0.stats, B, S, S, nf)
     idx = 3
     hs = [h0]
     nres = len(cfg.ch_mult)

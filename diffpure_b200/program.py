@@ -118,6 +118,19 @@ class Program:
     def conv_in(self, w, bias, out, stats, B, H, W, Cout):
         self.add("conv_in", w=view(w), bias=view(bias), out=view(out), stats=view(stats), B=B, H=H, W=W, Cout=Cout)
 
+    def conv_in_gemm(self, name, w_oc33, bias, out, stats, B, H, W, Cout):
+        """The 3 -> C input conv on the tensor cores: the state is cast to bf16 and zero-padded to 64 channels (`pad_in`),
+        the weights to K = 9 * 64 (27 non-zero columns); bias, fp32 output and the GroupNorm partial statistics come from the
+        GEMM epilogue (no separate statistics kernel)."""
+        import torch
+        from .lowering_common import act_seg, pack_conv3x3
+        xin = self.tensor(name + ".x64", B * H * W * 64, "bf16")
+        self.add("pad_in", out=view(xin), B=B, H=H, W=W, Cpad=64)
+        w64 = torch.zeros(Cout, 64, 3, 3)
+        w64[:, :w_oc33.shape[1]] = w_oc33.detach().float().cpu()
+        self.gemm([act_seg(xin, 64, taps=9)], self.const_bf16(name + ".w", pack_conv3x3(w64)), Cout, 9 * 64, B, H, W, Cout,
+                  bias=self.const_f32(name + ".b", bias), out_f32=out, stats=stats)
+
     def update(self, eps, ld, B, H, W, Cout):
         self.add("update", eps=view(eps), ld=ld, B=B, H=H, W=W, Cout=Cout)
 

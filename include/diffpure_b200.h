@@ -208,6 +208,13 @@ int dp_op_transpose(dp_engine* e, const dp_transpose_desc* d);
 int dp_op_attn_small_bwd(dp_engine* e, const dp_attn_small_bwd_desc* d);
 int dp_op_grad_in(dp_engine* e, const dp_grad_in_desc* d);
 
+/* The engine's state x (fp32, 3 channels) as a bf16 NHWC tensor zero-padded to Cpad channels: the A operand of the 3->C
+ * input conv (ncsnpp.py:268, unet.py:486, unet_ddpm.py:229) when it runs as a dp_op_gemm on the tensor cores. */
+typedef struct {
+  void* out_bf16; int B, H, W, Cpad;
+} dp_pad_in_desc;
+int dp_op_pad_in(dp_engine* e, const dp_pad_in_desc* d);
+
 int dp_op_embed(dp_engine* e, const dp_embed_desc* d);
 int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d);
 int dp_op_gn_apply(dp_engine* e, const dp_gn_desc* d);
@@ -272,7 +279,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
  * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 attn_small,7 softmax_rows,8 update,
- * 9 gn_bwd,10 softmax_bwd,11 transpose,12 attn_small_bwd,13 grad_in,14 gn_finalize,
+ * 9 gn_bwd,10 softmax_bwd,11 transpose,12 attn_small_bwd,13 grad_in,14 gn_finalize,15 pad_in,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 

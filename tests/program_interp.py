@@ -228,6 +228,11 @@ class Interp:
             sb, so = self.flat(stats)
             sb[so:so + st.numel()] = st.reshape(-1)
 
+    def op_pad_in(self, out, B, H, W, Cpad):
+        x = torch.zeros(B, H, W, Cpad)
+        x[..., :3] = self.x.permute(0, 2, 3, 1)
+        self.wr(out, x, (B, H, W, Cpad), (H * W * Cpad, W * Cpad, Cpad, 1))
+
     def op_update(self, eps, ld, B, H, W, Cout):
         e = self.rd(eps, (B, H, W, Cout), (H * W * ld, W * ld, ld, 1))
         self.out = e.permute(0, 3, 1, 2).contiguous()

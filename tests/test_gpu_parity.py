@@ -51,7 +51,7 @@ def test_unet_eval_cifar10_golden():
     sd = weights.make_state_dict(O.param_shapes(O.CIFAR10_CFG), seed=int(d["seed"]))
     eng = engine_for(O.CIFAR10_CFG, sd, d["x"].shape[0])
     y = eng.unet_forward(d["x"].cuda(), d["labels"].cuda()).cpu()
-    assert eng.launches_per_eval == 328   # 203 GEMMs (103 with a fused GroupNorm epilogue) + 60 x (gn_finalize + gn_apply) + conv_in, stats, update, embed, attn_small
+    assert eng.launches_per_eval == 328   # 204 GEMMs (103 with a fused GroupNorm epilogue; the input conv is one of them) + 60 x (gn_finalize + gn_apply) + pad_in, update, embed, attn_small
     assert eng.fused_gn_gemms == 103    # 76 x GroupNorm_1 (resident accumulators) + 27 x the next block's GroupNorm_0 (late; 3x3 convs at <= 16x16)
     eng.close()
     assert rel(y, d["y"]) < TOL_EVAL, rel(y, d["y"])
