@@ -1,7 +1,9 @@
-// dp_elem.cu -- bandwidth-bound kernels around the tcgen05 GEMMs (sm_100a): GroupNorm apply (+SiLU, FiLM,
-// resample, concat) producing the bf16 GEMM operands, GroupNorm statistics, timestep embedding, the 3->C input
-// conv, the C->3|6 output conv fused with the per-step SDE / DDPM update, short-sequence attention, layout
-// conversion. All activations are NHWC; vector width is 8 channels (32 B fp32 in, 16 B bf16 out).
+// dp_elem.cu -- bandwidth-bound kernels around the tcgen05 GEMMs (sm_100a): GroupNorm finalize / apply (+SiLU, FiLM,
+// resample, concat) producing the bf16 GEMM operands where the GroupNorm is not fused into the producing GEMM's epilogue,
+// GroupNorm statistics, timestep embedding, the state cast for the tensor-core input conv (and the SIMT input conv it
+// replaced), the stand-alone per-step update (forward-mode output; the step graph applies the update in the output conv's
+// epilogue, dp_gemm.cu), short-sequence attention, row softmax, the fused pre / post steps and layout conversion.
+// All activations are NHWC; vector width is 8 channels (32 B fp32 in, 16 B bf16 out).
 #include <cstdlib>
 
 #include "dp_elem.cuh"

@@ -628,6 +628,15 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     }
   }
   p.num_stages = dp::gemm_max_stages(bn, op.cg, p.gn_out != nullptr);
+  {
+    // shared row patches for the 3x3 taps (halves the A bytes fetched from L2 at 32x32; DP_GEMM_PATCH=0 disables)
+    static const int patch_on = [] { const char* v = std::getenv("DP_GEMM_PATCH"); return v ? std::atoi(v) : 1; }();
+    if (patch_on && dp::gemm_enable_patch(p, bn, op.cg)) {
+      const dp_gemm_aseg& a0 = d->a[0];
+      if (dp::make_act_tmap(&p.a[0].tmap, a0.act_bf16, a0.c_total, a0.c_total, d->W, d->H, d->B, tb.bw, tb.bh + 2, 1, 1, &err))
+        return fail(e, DP_ERR_CUDA, "gemm: A patch tensor map: " + err);
+    }
+  }
   if (dp::make_mat_tmap(&p.tmap_b, d->w_bf16, d->w_cols > 0 ? d->w_cols : ktotal, d->w_rows, d->w_pitch, bn / op.cg,
                         &err))
     return fail(e, DP_ERR_CUDA, "gemm: B tensor map: " + err);

@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
   if ((base & 1023u) != 0u) __trap();
 
   const int stages = p.num_stages;
-  float* staging = reinterpret_cast<float*>(sm + static_cast<size_t>(stages) * L::kStageBytes);
+  const int stage_bytes = p.stage_bytes ? p.stage_bytes : L::kStageBytes;     // patch mode: one A row patch + 3 weight tiles
+  const int b_off = p.stage_bytes ? p.a_patch_bytes : kStageABytes;            // weight tile(s) behind the A tile / patch
+  float* staging = reinterpret_cast<float*>(sm + static_cast<size_t>(stages) * stage_bytes);
   float* sstats = staging + L::kStagingFloats;
   constexpr int EW = epi_warps(BN, kGN);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sstats + L::kStatsFloats + (kGN ? L::kGnFloats : 0));
@@ -174,8 +176,8 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
   const int total_units = (p.m_tiles / (CG * tpg * p.upc)) * p.n_tiles * p.batch;
   const int ns_mask = p.acc_stages - 1;                 // accumulator stage of the it-th tile = it & ns_mask,
   const int ns_shift = p.acc_stages == 4 ? 2 : 1;       // its barrier parity = (it >> ns_shift) & 1
-  int num_kb = 0;
-  for (int s = 0; s < p.nseg; ++s) num_kb += p.a[s].taps * p.a[s].kchunks;
+  int num_kb = 0;  // pipeline stages consumed per tile
+  for (int s = 0; s < p.nseg; ++s) num_kb += (p.a[s].patch ? 3 : p.a[s].taps) * p.a[s].kchunks;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -191,6 +193,37 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
         const int b_k0 = c.hd * p.b_inner_k;
         for (int s = 0; s < p.nseg; ++s) {
           const GemmASeg& seg = p.a[s];
+          if (seg.patch) {
+            // one stage = the row patch of horizontal shift kx for one 64-channel chunk + the weight tiles of its 3 taps
+            const int c2 = c.h0 - 1;
+            for (int kc = 0; kc < seg.kchunks; ++kc)
+              for (int kx = 0; kx < 3; ++kx) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sa = base + stage * stage_bytes;
+                const int c1 = c.w0 + kx - 1;
+                const int ctap = seg.kchunks * kBlockK;  // K columns per tap
+                if constexpr (CG == 2) {
+                  if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
+                  const uint32_t sig = mapa_u32(full_bar(stage), 0);
+                  tma_load_4d_pair(sa, &seg.tmap, sig, a_k0 + kc * kBlockK, c1, c2, c.n0);
+                  for (int ky = 0; ky < 3; ++ky)
+                    tma_load_2d_pair(sa + b_off + ky * L::kStageBBytes, &p.tmap_b, sig,
+                                     b_k0 + kglobal + (ky * 3 + kx) * ctap + kc * kBlockK, brow);
+                } else {
+                  mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                  tma_load_4d(sa, &seg.tmap, full_bar(stage), a_k0 + kc * kBlockK, c1, c2, c.n0);
+                  for (int ky = 0; ky < 3; ++ky)
+                    tma_load_2d(sa + b_off + ky * L::kStageBBytes, &p.tmap_b, full_bar(stage),
+                                b_k0 + kglobal + (ky * 3 + kx) * ctap + kc * kBlockK, brow);
+                }
+                if (++stage == stages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            kglobal += 9 * seg.kchunks * kBlockK;
+            continue;
+          }
           for (int tap = 0; tap < seg.taps; ++tap) {
             const int ky = (seg.taps == 9) ? tap / 3 : 0;
             const int kx = (seg.taps == 9) ? tap - 3 * ky : 0;
@@ -198,17 +231,18 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
             const int c2 = c.h0 * seg.stride + ky - seg.pad;
             for (int kc = 0; kc < seg.kchunks; ++kc) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t sa = base + stage * L::kStageBytes;
+              const uint32_t sa = base + stage * stage_bytes;
+              const uint32_t tile_bytes = kStageABytes + L::kStageBBytes;  // a plain stage inside a (larger) patch-mode slot
               if constexpr (CG == 2) {
                 // both CTAs' bytes are counted on the leader's barrier (the MMA issuer waits there)
-                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * tile_bytes);
                 const uint32_t sig = mapa_u32(full_bar(stage), 0);
                 tma_load_4d_pair(sa, &seg.tmap, sig, a_k0 + kc * kBlockK, c1, c2, c.n0);
-                tma_load_2d_pair(sa + kStageABytes, &p.tmap_b, sig, b_k0 + kglobal, brow);
+                tma_load_2d_pair(sa + b_off, &p.tmap_b, sig, b_k0 + kglobal, brow);
               } else {
-                mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+                mbar_arrive_expect_tx(full_bar(stage), tile_bytes);
                 tma_load_4d(sa, &seg.tmap, full_bar(stage), a_k0 + kc * kBlockK, c1, c2, c.n0);
-                tma_load_2d(sa + kStageABytes, &p.tmap_b, full_bar(stage), b_k0 + kglobal, brow);
+                tma_load_2d(sa + b_off, &p.tmap_b, full_bar(stage), b_k0 + kglobal, brow);
               }
               kglobal += kBlockK;
               if (++stage == stages) {
@@ -223,6 +257,8 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
   } else if (warp == 1 && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, BN);
+    const int n_patch = p.a[0].patch ? 3 * p.a[0].kchunks : 0;  // leading patch stages of a tile (segment 0 only)
+    const uint32_t patch_row_bytes = static_cast<uint32_t>(p.bw) * 128u;  // one image row of the tile inside a patch
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -237,14 +273,28 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
         mbar_wait(full_bar(stage), phase);
         tc_fence_after_sync();
         if (elect_one()) {
-          const uint32_t sa = base + stage * L::kStageBytes;
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageABytes);
+          const uint32_t sa = base + stage * stage_bytes;
+          if (kb < n_patch) {
+            // patch stage: taps (ky = 0..2, this stage's kx) read the row patch from row ky on; one weight tile per tap
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint64_t adesc = make_kmajor_sw128_desc(sa + ky * patch_row_bytes);
+              const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off + ky * L::kStageBBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if constexpr (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | ky | k) != 0 ? 1u : 0u);
+                else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | ky | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else {
+            const uint64_t adesc = make_kmajor_sw128_desc(sa);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sa + b_off);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              if constexpr (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (CG == 2) {  // frees the stage / publishes the accumulator in both CTAs
             umma_commit_pair(empty_bar(stage), 3);
@@ -639,7 +689,8 @@ int launch_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (total <= 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
   constexpr bool gn = (EPI & E_GN) != 0;
-  const size_t smem = Smem<BN, 1, gn>::total(p.num_stages);
+  const size_t smem = Smem<BN, 1, gn>::total(0) +
+                      static_cast<size_t>(p.num_stages) * (p.stage_bytes ? p.stage_bytes : Smem<BN, 1, gn>::kStageBytes);
   return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 1>, dim3(grid), dim3(num_threads(BN, gn)), smem, stream, 1, p));
 }
 
@@ -654,7 +705,8 @@ int launch_pair_t(const GemmParams& p, int num_sms, cudaStream_t stream) {
   const int pairs = upc * (total < slots ? total : slots);
   constexpr bool gn = (EPI & E_GN) != 0;
   return static_cast<int>(launch_k(gemm_kernel<BN, EPI, 2>, dim3(2 * pairs), dim3(num_threads(BN, gn)),
-                                   Smem<BN, 2, gn>::total(p.num_stages), stream, 2, p));
+                                   Smem<BN, 2, gn>::total(0) + static_cast<size_t>(p.num_stages) *
+                                       (p.stage_bytes ? p.stage_bytes : Smem<BN, 2, gn>::kStageBytes), stream, 2, p));
 }
 
 // epilogues of the convolutions, the only ops big enough for CTA pairs
@@ -728,6 +780,7 @@ int dispatch(const GemmParams& p, int mask, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
+
 size_t gemm_smem_bytes(int bn, int stages, int cg, bool gn) {
   if (gn) {
     if (cg == 2) return bn == 256 ? Smem<256, 2, true>::total(stages) : Smem<128, 2, true>::total(stages);
@@ -735,6 +788,26 @@ size_t gemm_smem_bytes(int bn, int stages, int cg, bool gn) {
   }
   if (cg == 2) return bn == 256 ? Smem<256, 2>::total(stages) : Smem<128, 2>::total(stages);
   return bn == 256 ? Smem<256>::total(stages) : (bn == 32 ? Smem<32>::total(stages) : Smem<128>::total(stages));
+}
+
+// Patch mode (GemmParams::stage_bytes): enable it for segment 0 when the shape allows and at least two stages fit.
+// The caller builds segment 0's tensor map with a (64, bw, bh + 2, 1) box afterwards.
+bool gemm_enable_patch(GemmParams& p, int bn, int cg) {
+  const GemmASeg& a = p.a[0];
+  if (a.taps != 9 || a.stride != 1 || a.pad != 1 || p.imgs_per_tile != 1 || p.batch != 1 || p.H < 2 ||
+      (p.bw != 16 && p.bw != 32 && p.bw != 64) || p.bh < 2 || p.bw * p.bh != kBlockM || (bn != 128 && bn != 256))
+    return false;
+  const size_t cap = 232448;
+  const size_t patch = static_cast<size_t>(p.bh + 2) * p.bw * 128;
+  const size_t stage = patch + 3 * static_cast<size_t>(bn / cg) * kBlockK * 2;
+  const size_t rest = gemm_smem_bytes(bn, 0, cg, p.gn_out != nullptr);
+  const int stages = static_cast<int>((cap - rest) / stage);
+  if (stages < 2) return false;
+  p.a[0].patch = 1;
+  p.a_patch_bytes = static_cast<int>(patch);
+  p.stage_bytes = static_cast<int>(stage);
+  p.num_stages = stages < kMaxStages ? stages : kMaxStages;
+  return true;
 }
 
 int gemm_max_stages(int bn, int cg, bool gn) {

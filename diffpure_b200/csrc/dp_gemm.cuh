@@ -24,7 +24,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 
 struct GemmASeg {
-  CUtensorMap tmap;  // (C, W, H, B) bf16, box (64, bw, bh, bn), SWIZZLE_128B
+  CUtensorMap tmap;  // (C, W, H, B) bf16, box (64, bw, bh, bn), SWIZZLE_128B; patch mode: box (64, bw, bh + 2, 1)
+  int patch;         // 1: 3x3 taps read from shared row patches (see GemmParams::stage_bytes)
   int taps;          // 1 or 9
   int kchunks;       // C / 64
   int stride;        // coordinate multiplier (2 for the stride-2 downsample conv)
@@ -52,6 +53,15 @@ struct GemmParams {
   int b_inner_rows;      // B row offset per head
   long long out_inner_stride;  // output element offset per head
   int num_stages;
+  // Patch mode of a 3x3 segment (stride 1, one image per tile, W in {16, 32, 64}): the nine taps of a 64-channel chunk are
+  // NOT nine 16 KiB TMA tiles (each A byte fetched from L2 nine times -- the N = 128 convolutions ran at the L2 throughput cap,
+  // 47 B/clk/SM of the chip's ~43) but three row patches, one per horizontal shift kx: box (64, bw, bh + 2, 1) = the tile's rows
+  // plus one above and one below; the tap (ky, kx) operand is the patch from row ky on -- a plain K-major tile at a
+  // 1024-byte-aligned offset ky * bw * 128 B. A stage then holds one patch + the three weight tiles of its taps: A bytes
+  // from L2 drop by 9 bh / (3 (bh + 2)) = 2x at 32x32, 2.4x at 16x16. stage_bytes == 0: every stage is one 16 KiB A tile +
+  // one weight tile.
+  int stage_bytes;    // bytes per pipeline stage in patch mode (a_patch_bytes + 3 weight tiles), multiple of 1024
+  int a_patch_bytes;  // (bh + 2) * bw * 128
   // ---- epilogue ----
   const float* bias;  // [N] (or [M] if bias_along_m)
   int bias_along_m;
@@ -114,6 +124,10 @@ bool gemm_pair_supported(const GemmParams& p, int bn, bool softmax);
 // (p.gn_out != nullptr) carry a scale/shift table and the pair exchange buffers.
 size_t gemm_smem_bytes(int bn, int stages, int cg = 1, bool gn = false);
 int gemm_max_stages(int bn, int cg = 1, bool gn = false);
+// Switches segment 0 (a stride-1 3x3 conv on one-image tiles with W in {16, 32, 64}) to patch mode when two or more of its
+// stages fit in shared memory: fills a[0].patch, a_patch_bytes, stage_bytes, num_stages (geometry and gn_out must be set).
+// The caller then builds a[0].tmap with a (64, bw, bh + 2, 1) box.
+bool gemm_enable_patch(GemmParams& p, int bn, int cg);
 // One-time cudaFuncSetAttribute for all instantiations.
 int gemm_init();
 

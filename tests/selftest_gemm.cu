@@ -156,6 +156,17 @@ static void run_conv(const ConvCase& cs) {
     failures++;
     return;
   }
+  // shared row patches for the 3x3 taps wherever the shape allows (DP_SELFTEST_PATCH=0: the tile-per-tap mainloop)
+  static const bool patch_on = !(getenv("DP_SELFTEST_PATCH") && atoi(getenv("DP_SELFTEST_PATCH")) == 0);
+  bool patched = false;
+  if (patch_on && dp::gemm_enable_patch(p, cs.bn, cg)) {
+    patched = true;
+    if (dp::make_act_tmap(&p.a[0].tmap, d_a0, cs.C0, cs.C0, Win, Hin, B, tb.bw, tb.bh + 2, 1, 1, &err)) {
+      printf("[%s] tmap a0 patch: %s\n", cs.name, err.c_str());
+      failures++;
+      return;
+    }
+  }
   p.bias = cs.bias ? d_bias : nullptr;
   p.rowvec = cs.rowvec ? d_rowvec : nullptr;
   p.rowvec_ld = N;
@@ -268,8 +279,8 @@ static void run_conv(const ConvCase& cs) {
   }
   const bool ok = maxerr <= 2e-3 * fmax(1.0, maxref) && (!(cs.out_bf16 || cs.gn) || maxerr_b <= 1e-2 * fmax(1.0, maxref)) &&
                   (!cs.stats || cs.gn == 1 || maxs <= 1e-3 * fmax(1.0, maxsref));
-  printf("[%s] %s  max|err|=%.3e (max|ref|=%.3f) bf16out err=%.3e stats err=%.3e (ref %.2f)\n", cs.name,
-         ok ? "OK  " : "FAIL", maxerr, maxref, maxerr_b, maxs, maxsref);
+  printf("[%s]%s %s  max|err|=%.3e (max|ref|=%.3f) bf16out err=%.3e stats err=%.3e (ref %.2f)\n", cs.name,
+         patched ? " (row patches)" : "", ok ? "OK  " : "FAIL", maxerr, maxref, maxerr_b, maxs, maxsref);
   if (!ok) failures++;
   cudaFree(d_a0); cudaFree(d_a1); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_rowvec); cudaFree(d_resid);
   cudaFree(d_out); cudaFree(d_outb); cudaFree(d_stats); cudaFree(d_gamma); cudaFree(d_beta); cudaFree(d_gn);
@@ -378,6 +389,7 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
   p.a[0].taps = taps; p.a[0].kchunks = C0 / 64; p.a[0].stride = 1; p.a[0].pad = taps == 9 ? 1 : 0; p.nseg = 1;
   if (dp::make_mat_tmap(&p.tmap_b, d_w, Kt, N, Kt, bn / cg, &err)) { printf("%s\n", err.c_str()); exit(1); }
   p.bias = d_bias; p.alpha = 1.f; p.out_f32 = d_out; p.ldc = N; p.stats = d_stats;
+  const bool want_patch = !(getenv("DP_SELFTEST_PATCH") && atoi(getenv("DP_SELFTEST_PATCH")) == 0);
   if (getenv("DP_PERF_BF16")) { p.out_f32 = nullptr; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d_out); }  // bf16 output epilogue
   if (getenv("DP_PERF_GN")) {  // fused GroupNorm + SiLU epilogue (bf16 output only)
     p.out_f32 = nullptr; p.out_bf16 = nullptr; p.stats = nullptr;
@@ -399,6 +411,11 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
   }
   int sh = 0; while ((1 << sh) < H * W) ++sh;
   if (resid) { p.resid = d_res; p.alpha = 0.70710678f; } else { p.rowvec = d_rowvec; p.rowvec_ld = N; p.rowvec_shift = sh; }
+  bool patched = false;
+  if (want_patch && dp::gemm_enable_patch(p, bn, cg)) {   // after the epilogue kind (gn_out) is known: it sizes the stages
+    patched = true;
+    if (dp::make_act_tmap(&p.a[0].tmap, d_a, C0, C0, W, H, B, tb.bw, tb.bh + 2, 1, 1, &err)) { printf("%s\n", err.c_str()); exit(1); }
+  }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) {
     int e = dp::launch_gemm(p, bn, false, num_sms, 0, cg);
@@ -412,7 +429,8 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
   CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   const double fl = 2.0 * M * N * Kt;
-  printf("perf B%d %dx%d C%d taps%d N%d bn%d cg%d resid%d: %.1f us  %.1f TF/s\n", B, H, W, C0, taps, N, bn, cg, resid, ms / iters * 1e3, fl / (ms / iters * 1e-3) / 1e12);
+  printf("perf B%d %dx%d C%d taps%d N%d bn%d cg%d resid%d%s stages=%d: %.1f us  %.1f TF/s\n", B, H, W, C0, taps, N, bn, cg, resid,
+         patched ? " patch" : "", p.num_stages, ms / iters * 1e3, fl / (ms / iters * 1e-3) / 1e12);
 }
 
 int main(int argc, char** argv) {

@@ -41,9 +41,11 @@ def test_gemm_kernel_selftest():
     """tcgen05 implicit-GEMM kernel vs a host loop: conv 3x3 / 1x1 / stride 2, fused shortcut, statistics,
     ragged M, 2 and 8 images per tile, batched attention GEMMs with the softmax epilogue."""
     exe = os.path.join(ROOT, "diffpure_b200", "selftest_gemm")
-    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
-    assert "0 failure(s)" in res.stdout
+    for patch in ("1", "0"):      # 3x3 taps from shared row patches (default) and the tile-per-tap mainloop
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, DP_SELFTEST_PATCH=patch))
+        assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+        assert "0 failure(s)" in res.stdout
+        assert ("(row patches)" in res.stdout) == (patch == "1")
 
 
 def test_unet_eval_cifar10_golden():
