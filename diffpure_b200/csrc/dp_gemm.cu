@@ -224,12 +224,17 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
             kglobal += 9 * seg.kchunks * kBlockK;
             continue;
           }
-          for (int tap = 0; tap < seg.taps; ++tap) {
-            const int ky = (seg.taps == 9) ? tap / 3 : 0;
-            const int kx = (seg.taps == 9) ? tap - 3 * ky : 0;
-            const int c1 = c.w0 * seg.stride + kx - seg.pad + c.bo * p.a_batch_rows + c.hd * p.a_inner_rows;
-            const int c2 = c.h0 * seg.stride + ky - seg.pad;
-            for (int kc = 0; kc < seg.kchunks; ++kc) {
+          // tile-per-tap stages. A 3x3 segment walks (chunk, kx, ky) exactly as the patch mode does, so both mainloops
+          // accumulate in the same order and give bit-identical results whichever one a tile shape selects.
+          const int ntap = seg.taps;
+          const int ctap = seg.kchunks * kBlockK;  // K columns per tap
+          for (int kc = 0; kc < seg.kchunks; ++kc)
+            for (int t9 = 0; t9 < ntap; ++t9) {
+              const int kx = (ntap == 9) ? t9 / 3 : 0;
+              const int ky = (ntap == 9) ? t9 - 3 * kx : 0;
+              const int c1 = c.w0 * seg.stride + kx - seg.pad + c.bo * p.a_batch_rows + c.hd * p.a_inner_rows;
+              const int c2 = c.h0 * seg.stride + ky - seg.pad;
+              const int bk = b_k0 + kglobal + (ky * 3 + kx) * ctap + kc * kBlockK;
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = base + stage * stage_bytes;
               const uint32_t tile_bytes = kStageABytes + L::kStageBBytes;  // a plain stage inside a (larger) patch-mode slot
@@ -238,19 +243,18 @@ __global__ void __launch_bounds__(num_threads(BN, (EPI & E_GN) != 0), 1) gemm_ke
                 if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * tile_bytes);
                 const uint32_t sig = mapa_u32(full_bar(stage), 0);
                 tma_load_4d_pair(sa, &seg.tmap, sig, a_k0 + kc * kBlockK, c1, c2, c.n0);
-                tma_load_2d_pair(sa + b_off, &p.tmap_b, sig, b_k0 + kglobal, brow);
+                tma_load_2d_pair(sa + b_off, &p.tmap_b, sig, bk, brow);
               } else {
                 mbar_arrive_expect_tx(full_bar(stage), tile_bytes);
                 tma_load_4d(sa, &seg.tmap, full_bar(stage), a_k0 + kc * kBlockK, c1, c2, c.n0);
-                tma_load_2d(sa + b_off, &p.tmap_b, full_bar(stage), b_k0 + kglobal, brow);
+                tma_load_2d(sa + b_off, &p.tmap_b, full_bar(stage), bk, brow);
               }
-              kglobal += kBlockK;
               if (++stage == stages) {
                 stage = 0;
                 phase ^= 1u;
               }
             }
-          }
+          kglobal += ntap * ctap;
         }
       }
     }
