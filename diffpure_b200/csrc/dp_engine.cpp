@@ -437,6 +437,15 @@ int dp_op_embed(dp_engine* e, const dp_embed_desc* d) {
   return DP_OK;
 }
 
+// DP_GEMM_BN256: 1 (default) = 256-wide tiles wherever the heuristics below allow; 0 = never; 2 = not for 3x3 convolutions at
+// 16x16 / 32x32 / 64x64, where BN = 128 tiles can use the row-patch mainloop (A/B switch)
+static bool bn256_mode(const dp_gemm_desc* d, int hw) {
+  static const int mode = [] { const char* v = std::getenv("DP_GEMM_BN256"); return v ? std::atoi(v) : 1; }();
+  if (mode == 0) return false;
+  if (mode == 2 && d->a[0].taps == 9 && d->a[0].stride == 1 && (d->W == 16 || d->W == 32 || d->W == 64) && hw >= 128) return false;
+  return true;
+}
+
 int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
   if (!e || !d) return DP_ERR_INVALID;
   if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
@@ -542,7 +551,7 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     bn = 32;  // narrow output (the C->3|6 conv padded to 8 columns): 128x32 tiles waste 4x instead of 16x of the MMA
   } else if (gn_fused && hw == 1024 && !d->out_f32) {
     bn = 128;  // four resident accumulator stages need BN = 128
-  } else if (d->N % 256 == 0 && kprobe > 512) {
+  } else if (d->N % 256 == 0 && kprobe > 512 && bn256_mode(d, hw) ) {
     // (K <= 512: four to eight k-blocks per tile, the epilogue dominates and the 8-warp BN = 128 epilogue wins: measured
     //  80 vs 90 us and 107 vs 159 us on the 16x16 attention projections, tests/selftest_gemm perf)
     dp::GemmParams probe;
