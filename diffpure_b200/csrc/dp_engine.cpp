@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "dp_attn.cuh"
 #include "dp_elem.cuh"
 #include "dp_gemm.cuh"
 #include "dp_tmap.h"
@@ -20,7 +21,7 @@ namespace {
 std::string g_create_error;
 
 enum OpKind { OP_EMBED, OP_GEMM, OP_GN, OP_STATS, OP_STATS_REDUCE, OP_CONV_IN, OP_ATTN_SMALL, OP_SOFTMAX, OP_UPDATE,
-              OP_GN_BWD, OP_SOFTMAX_BWD, OP_TRANSPOSE, OP_ATTN_SMALL_BWD, OP_GRAD_IN, OP_GN_FINALIZE, OP_PAD_IN };
+              OP_GN_BWD, OP_SOFTMAX_BWD, OP_TRANSPOSE, OP_ATTN_SMALL_BWD, OP_GRAD_IN, OP_GN_FINALIZE, OP_PAD_IN, OP_ATTN_BLOCK };
 
 struct StatsReduce {
   const float* in;
@@ -56,6 +57,7 @@ struct Op {
   dp::AttnSmallBwdParams attnb;
   dp_grad_in_desc gin;
   dp_pad_in_desc pin;
+  dp::AttnBlockParams ablk;
 };
 
 }  // namespace
@@ -227,6 +229,9 @@ int run_op(dp_engine* e, size_t i, int mode, cudaStream_t s) {
       rc = dp::launch_grad_in(e->g_in, static_cast<__nv_bfloat16*>(op.gin.out_bf16), op.gin.B, op.gin.C,
                               op.gin.H * op.gin.W, op.gin.Cpad, s);
       break;
+    case OP_ATTN_BLOCK:
+      rc = dp::launch_attn_block(op.ablk, e->num_sms, s);
+      break;
     case OP_SOFTMAX:
       rc = dp::launch_softmax_rows(op.smax.src, static_cast<__nv_bfloat16*>(op.smax.out_bf16), op.smax.rows,
                                    op.smax.T, s);
@@ -303,6 +308,11 @@ int dp_create(dp_engine** out, int device) {
   int rc = dp::gemm_init();
   if (rc) {
     g_create_error = std::string("gemm_init: ") + cudaGetErrorString(static_cast<cudaError_t>(rc));
+    return DP_ERR_CUDA;
+  }
+  rc = dp::attn_block_init();
+  if (rc) {
+    g_create_error = std::string("attn_block_init: ") + cudaGetErrorString(static_cast<cudaError_t>(rc));
     return DP_ERR_CUDA;
   }
   dp_engine* e = new dp_engine();
@@ -752,6 +762,31 @@ int dp_op_attn_small(dp_engine* e, const dp_attn_small_desc* d) {
   return DP_OK;
 }
 
+int dp_op_attn_block(dp_engine* e, const dp_attn_block_desc* d) {
+  if (!e || !d) return DP_ERR_INVALID;
+  if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
+  if (d->T != dp::kAttnBlockT || d->C != dp::kAttnBlockC || d->B <= 0)
+    return fail(e, DP_ERR_INVALID, "attn_block: the fused attention block is built for T = 256 tokens of C = 256 channels");
+  if (!d->hn_bf16 || !d->w_bf16 || !d->bias || !d->resid || !d->out_f32)
+    return fail(e, DP_ERR_INVALID, "attn_block: hn, w, bias, resid and out are required");
+  Op op;
+  op.kind = OP_ATTN_BLOCK;
+  dp::AttnBlockParams& a = op.ablk;
+  std::string err;
+  if (dp::make_mat_tmap(&a.tmap_h, d->hn_bf16, d->C, static_cast<long long>(d->B) * d->T, d->C, 128, &err) ||
+      dp::make_mat_tmap(&a.tmap_w, d->w_bf16, d->C, 4LL * d->C, d->C, 128, &err))
+    return fail(e, DP_ERR_CUDA, "attn_block: " + err);
+  a.bias = d->bias;
+  a.resid = d->resid;
+  a.out_f32 = d->out_f32;
+  a.stats = d->stats;
+  a.B = d->B;
+  a.scale = d->scale;
+  a.alpha = d->alpha;
+  e->ops.push_back(op);
+  return DP_OK;
+}
+
 int dp_op_softmax_rows(dp_engine* e, const dp_softmax_desc* d) {
   if (!e || !d) return DP_ERR_INVALID;
   if (e->finalized) return fail(e, DP_ERR_STATE, "program already finalized");
@@ -1066,6 +1101,8 @@ int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops,
       double k = 0;
       for (int s2 = 0; s2 < g.nseg; ++s2) k += 64.0 * g.a[s2].taps * g.a[s2].kchunks;
       flops[i] = 2.0 * g.M * g.N * k * g.batch;
+    } else if (e->ops[i].kind == OP_ATTN_BLOCK) {  // six T x C x C GEMMs per sample (T = C)
+      flops[i] = 6.0 * 2.0 * dp::kAttnBlockT * dp::kAttnBlockC * dp::kAttnBlockC * e->ops[i].ablk.B;
     }
   }
   for (auto& x : ev) cudaEventDestroy(x);

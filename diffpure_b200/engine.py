@@ -213,6 +213,11 @@ class Engine:
                 d = _lib.AttnSmallDesc(self._p(a["qkv"]), self._p(a["out"]), a["B"], a["T"], a["heads"], a["d"],
                                        a["scale"])
                 self._check(L.dp_op_attn_small(self.h, C.byref(d)), "dp_op_attn_small")
+            elif op.kind == "attn_block":
+                d = _lib.AttnBlockDesc(self._p(a["hn"]), self._p(a["w"]), self._p(a["bias"]), self._p(a["resid"]),
+                                       self._p(a["out_f32"]), self._p(a["stats"]), a["B"], a["T"], a["C"], a["scale"],
+                                       a["alpha"])
+                self._check(L.dp_op_attn_block(self.h, C.byref(d)), "dp_op_attn_block")
             elif op.kind == "update":
                 d = _lib.UpdateDesc(self._p(a["eps"]), a["ld"], a["B"], a["H"], a["W"], a["Cout"])
                 self._check(L.dp_op_update(self.h, C.byref(d)), "dp_op_update")
@@ -347,7 +352,7 @@ class Engine:
         return out
 
     OP_KINDS = ("embed", "gemm", "gn_apply", "stats", "stats_reduce", "conv_in", "attn_small",
-                "softmax_rows", "update", "gn_bwd", "softmax_bwd", "transpose", "attn_small_bwd", "grad_in", "gn_finalize", "pad_in")
+                "softmax_rows", "update", "gn_bwd", "softmax_bwd", "transpose", "attn_small_bwd", "grad_in", "gn_finalize", "pad_in", "attn_block")
 
     def profile_ops(self, mode=0):
         """Per-op device time (ms), kind and executed GEMM flops of one eagerly-run UNet evaluation."""

@@ -102,6 +102,12 @@ class PadInDesc(C.Structure):
     _fields_ = [("out_bf16", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cpad", C.c_int)]
 
 
+class AttnBlockDesc(C.Structure):
+    _fields_ = [("hn_bf16", C.c_void_p), ("w_bf16", C.c_void_p), ("bias", C.c_void_p), ("resid", C.c_void_p),
+                ("out_f32", C.c_void_p), ("stats", C.c_void_p), ("B", C.c_int), ("T", C.c_int), ("C", C.c_int),
+                ("scale", C.c_float), ("alpha", C.c_float)]
+
+
 class PurifyParams(C.Structure):
     _fields_ = [("steps", C.c_int), ("update_kind", C.c_int), ("ncoef", C.c_int), ("cond", C.c_void_p),
                 ("coef", C.c_void_p), ("init_scale_x", C.c_float), ("init_scale_e", C.c_float),
@@ -130,6 +136,7 @@ SYMBOLS = {
     "dp_op_stats": (C.c_int, [C.c_void_p, C.POINTER(StatsDesc)]),
     "dp_op_conv_in": (C.c_int, [C.c_void_p, C.POINTER(ConvInDesc)]),
     "dp_op_attn_small": (C.c_int, [C.c_void_p, C.POINTER(AttnSmallDesc)]),
+    "dp_op_attn_block": (C.c_int, [C.c_void_p, C.POINTER(AttnBlockDesc)]),
     "dp_op_softmax_rows": (C.c_int, [C.c_void_p, C.POINTER(SoftmaxDesc)]),
     "dp_op_update": (C.c_int, [C.c_void_p, C.POINTER(UpdateDesc)]),
     "dp_op_gn_bwd": (C.c_int, [C.c_void_p, C.POINTER(GnBwdDesc)]),

@@ -168,6 +168,12 @@ class Program:
     def grad_in(self, out, B, H, W, C, Cpad):
         self.add("grad_in", out=view(out), B=B, H=H, W=W, C=C, Cpad=Cpad)
 
+    def attn_block(self, hn, w, bias, resid, out_f32, stats, B, T, C, scale, alpha):
+        """AttnBlockpp behind its GroupNorm as one kernel (layerspp.py:75-91): w = Wq | Wk | Wv | W3 as [4C, C] ([out, in]),
+        bias = bq | bk | bv | b3; out = (resid + NIN_3(softmax(q k^T scale) v)) * alpha (+ partial statistics of out)."""
+        self.add("attn_block", hn=view(hn), w=view(w), bias=view(bias), resid=view(resid), out_f32=view(out_f32),
+                 stats=view(stats), B=B, T=T, C=C, scale=float(scale), alpha=float(alpha))
+
     def attn_small(self, qkv, out, B, T, heads, d, scale):
         self.add("attn_small", qkv=view(qkv), out=view(out), B=B, T=T, heads=heads, d=d, scale=float(scale))
 

@@ -23,6 +23,7 @@
  *                        guided_diffusion/gaussian_diffusion.py:240-334,403-447; runners/diffpure_ddpm.py:37-54;
  *                        runners/diffpure_ode.py:90-131; runners/diffpure_ldsde.py:92-148)
  *   dp_op_attn_small <- whole-sequence attention for short sequences (T <= 64)
+ *   dp_op_attn_block <- the whole attention block (projections, softmax, output projection, residual) for T = C = 256
  * Threading: one engine per (process, device); calls on an engine are stream-ordered and not re-entrant.
  * Ownership: the caller owns every pointer it passes to dp_unet_forward / dp_purify; the engine owns
  * buffers obtained from dp_buffer_alloc, its tensor maps and CUDA graphs.
@@ -157,6 +158,22 @@ typedef struct {
   int B, H, W, Cout;
 } dp_update_desc;
 
+/* The whole AttnBlockpp behind its GroupNorm (score_sde/models/layerspp.py:75-91: NIN_0..2, einsum . C^-1/2, softmax,
+ * einsum, NIN_3, (x + h) / sqrt 2) as ONE kernel for T = H*W = 256 tokens of C = 256 channels: q, k, v, the logits and P
+ * stay in tensor memory / shared memory of a CTA pair; replaces four dp_op_gemm launches + the output projection. */
+typedef struct {
+  const void* hn_bf16;  /* GroupNorm_0(x), bf16 [B*T, C] */
+  const void* w_bf16;   /* bf16 [4*C, C]: Wq | Wk | Wv | W3, each [out, in] (NIN.W transposed) */
+  const float* bias;    /* [4*C]: bq | bk | bv | b3 */
+  const float* resid;   /* x, fp32 [B*T, C] */
+  float* out_f32;       /* (x + h) * alpha, fp32 [B*T, C] */
+  float* stats;         /* optional: per-(128-row tile, channel) (sum, sumsq) of out, [B*T/128][C][2] (as dp_gemm_desc.stats) */
+  int B, T, C;          /* T and C must be 256 */
+  float scale;          /* applied to q.k before softmax */
+  float alpha;
+} dp_attn_block_desc;
+int dp_op_attn_block(dp_engine* e, const dp_attn_block_desc* d);
+
 typedef struct {
   const void* qkv_bf16; /* [B*T, 3*heads*d]: q | k | v, each [heads][d] */
   void* out_bf16;       /* [B*T, heads*d] */
@@ -279,7 +296,7 @@ int dp_purify(dp_engine* e, const float* x0_nchw, float* out_nchw, const dp_puri
 /* Measurement aid: runs the program once, op by op (mode 0 = forward, 1 = step without advancing the step
  * counter), each launch bracketed by CUDA events on the engine's stream. ms[i] = device time of op i,
  * kinds[i] = 0 embed,1 gemm,2 gn_apply,3 stats,4 stats_reduce,5 conv_in,6 attn_small,7 softmax_rows,8 update,
- * 9 gn_bwd,10 softmax_bwd,11 transpose,12 attn_small_bwd,13 grad_in,14 gn_finalize,15 pad_in,
+ * 9 gn_bwd,10 softmax_bwd,11 transpose,12 attn_small_bwd,13 grad_in,14 gn_finalize,15 pad_in,16 attn_block,
  * flops[i] = 2*M*N*K*batch executed by GEMM op i (0 otherwise). */
 int dp_profile_ops(dp_engine* e, int mode, float* ms, int* kinds, double* flops, int cap);
 
