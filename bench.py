@@ -416,6 +416,12 @@ def roofline_of(eng, wl, B, value_per_gpu, nsteps):
                 "eval_ms_by_kind": {k: round(v[1], 4) for k, v in by_kind.items()},
                 "eval_launches_by_kind": {k: v[0] for k, v in by_kind.items()},
                 "whole_loop_frac_of_peak": value_per_gpu * nsteps * wl["flops"] / 1e12 / peak_tf}
+    ab = by_kind.get("attn_block")
+    if ab:   # the one-kernel attention blocks (dp_attn.cu): six 256^3 GEMMs per sample each, also on the tcgen05 pipe
+        roofline["attn_block"] = {"kernel": "dp::attn_block_kernel (cta_group::2, q/k/v/logits/P on chip)",
+                                  "launches_per_eval": ab[0], "ms_per_eval": round(ab[1], 4),
+                                  "achieved": ab[2] / (ab[1] / 1e3) / 1e12, "unit": "TFLOP/s"}
+        roofline["tensor_kernels_frac"] = (gemm_fl + ab[2]) / ((gemm_ms + ab[1]) / 1e3) / 1e12 / peak_tf
     traffic_path = os.path.join(ROOT, "profiles", "gemm_dram_bytes_per_launch.json")
     if os.path.exists(traffic_path):                           # DRAM bytes need ncu: taken from the committed capture
         with open(traffic_path) as f:

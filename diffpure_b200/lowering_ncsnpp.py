@@ -13,6 +13,7 @@ Fusions per res-block (reference: 2 GroupNorm + 2 SiLU + 2-3 conv + Linear + add
   gemm(Conv_1 3x3 [+ Conv_2 1x1 as extra K] + biases + residual + 1/sqrt(2) + next block's GN statistics)
 All per-block Dense_0(SiLU(temb)) projections are one GEMM per step.
 """
+import os
 from types import SimpleNamespace
 
 import torch
@@ -108,11 +109,13 @@ def param_shapes(cfg):
     return shapes
 
 
-def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
+def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True, fuse_attn=True):
     """Build the engine program for batch size B. `sd`: name -> fp32 torch tensor (CPU).
     h_bf16: store the Conv_0 output (only ever read by GroupNorm_1) in bf16 -- halves its HBM round trip; the
     GroupNorm statistics are still accumulated from the fp32 accumulator values.
     fuse_gn: GroupNorm_1 + act of every res-block in the epilogue of its Conv_0 GEMM (the conv result stays in TMEM).
+    fuse_attn: an attention block of T = 256 tokens x C = 256 channels (the 16x16 level of the CIFAR-10 model) as ONE
+    kernel (`attn_block`, dp_attn.cu) instead of five GEMM launches; DP_FUSE_ATTN=0 in the environment turns it off (A/B).
     tape: a list -> every block appends the tensors its data-gradient needs and the program stops in front of the
     output GroupNorm / conv (`lower_vjp` appends the backward ops)."""
     S = cfg.image_size
@@ -120,6 +123,7 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
     plan = module_plan(cfg)
     nf = cfg.nf
     temb_dim = 4 * nf
+    fuse_attn = fuse_attn and os.environ.get("DP_FUSE_ATTN", "1") != "0"
 
     def P(i, name):
         return sd[f"all_modules.{i}.{name}"].detach().float().cpu()
@@ -257,6 +261,14 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True):
                           B=B, H=H, W=W, groups=_groups(C), eps=1e-6, silu=0, out_bf16=hn)
         wq, wk, wv = (P(i, f"NIN_{j}.W").t().contiguous() for j in range(3))   # NIN: y = x.W + b, W is [in, out]
         bq, bk, bv = (P(i, f"NIN_{j}.b") for j in range(3))
+        if fuse_attn and tape is None and T == 256 and C == 256:
+            # the whole block behind the GroupNorm as one kernel (dp_attn.cu): q, k, v^T, the logits, P and o stay on chip
+            out = new_act(prog, name + ".out", B, C, H, W)
+            w3, b3 = P(i, "NIN_3.W").t().contiguous(), P(i, "NIN_3.b")
+            prog.attn_block(hn, prog.const_bf16(name + ".wqkv3", torch.cat([wq, wk, wv, w3], 0)),
+                            prog.const_f32(name + ".bqkv3", torch.cat([bq, bk, bv, b3])), x.t, out.t, out.stats,
+                            B, T, C, C ** -0.5, INV_SQRT2)
+            return out
         o = prog.tensor(name + ".o", B * T * C, "bf16")
         if T <= 64:
             qkv = prog.tensor(name + ".qkv", B * T * 3 * C, "bf16")

@@ -241,6 +241,25 @@ class Interp:
         x = self.rd(src, (rows, T))
         self.wr(out, torch.softmax(x, -1), (rows, T), (T, 1))
 
+    def op_attn_block(self, hn, w, bias, resid, out_f32, stats, B, T, C, scale, alpha):
+        """dp_attn.cu: q, k, v^T, P and o are rounded to bf16 where the kernel turns accumulators into operand tiles."""
+        r = _bf16 if self.bf else (lambda t: t)
+        h = self.rd(hn, (B, T, C))
+        W = self.rd(w, (4, C, C))
+        b = self.rd(bias, (4, C))
+        x = self.rd(resid, (B, T, C))
+        q = r((h @ W[0].t() + b[0]) * scale)
+        k = r(h @ W[1].t() + b[1])
+        v = r(h @ W[2].t() + b[2])
+        s = q @ k.transpose(1, 2)
+        p = r(torch.exp(s - s.amax(-1, keepdim=True)))
+        o = r((p @ v) / p.sum(-1, keepdim=True))
+        y = (o @ W[3].t() + b[3] + x) * alpha
+        self.wr(out_f32, y, (B, T, C), (T * C, C, 1))
+        if stats is not None:
+            t = y.reshape(B * T // 128, 128, C)
+            self.wr(stats, torch.stack([t.sum(1), (t * t).sum(1)], -1), (B * T // 128, C, 2), (C * 2, 2, 1))
+
     def op_attn_small(self, qkv, out, B, T, heads, d, scale):
         x = self.rd(qkv, (B, T, 3, heads, d))
         q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]                        # [B, T, heads, d]

@@ -48,12 +48,46 @@ def test_gemm_kernel_selftest():
         assert ("(row patches)" in res.stdout) == (patch == "1")
 
 
+def test_attn_block_kernel_selftest():
+    """The one-kernel attention block (dp_attn.cu) vs a host loop rounding to bf16 at the same points; more samples than
+    CTA pairs (the persistent loop wraps), partial statistics, bit-identical results per sample position and launch."""
+    exe = os.path.join(ROOT, "diffpure_b200", "selftest_attn")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "0 failure(s)" in res.stdout
+
+
+def test_fused_attention_block_matches_the_gemm_sequence_and_the_oracle():
+    """T = 256 tokens x C = 256 channels: the program with `attn_block` ops against the same network lowered to the
+    five-GEMM attention sequence, and both against the oracle (layerspp.py:75-91)."""
+    from diffpure_b200 import lowering_ncsnpp as L
+    from diffpure_b200.engine import Engine
+    cfg = O.tiny_cfg(128, (1, 2), 1, (16,), 32)
+    B = 5
+    sd = weights.make_state_dict(O.param_shapes(cfg), seed=11)
+    torch.manual_seed(3)
+    x = torch.rand(B, 3, 32, 32) * 2 - 1
+    t = torch.rand(B) * 999
+    y = O.forward(cfg, sd, x, t)
+    fused = Engine(L.lower(cfg, sd, B), device=0)
+    plain = Engine(L.lower(cfg, sd, B, fuse_attn=False), device=0)
+    assert plain.launches_per_eval - fused.launches_per_eval == 3 * 4
+    yf = fused.unet_forward(x.cuda(), t.cuda()).cpu()
+    yp = plain.unet_forward(x.cuda(), t.cuda()).cpu()
+    fused.close()
+    plain.close()
+    assert rel(yf, y) < TOL_EVAL and rel(yp, y) < TOL_EVAL, (rel(yf, y), rel(yp, y))
+    assert rel(yf, yp) < 5e-3, rel(yf, yp)
+
+
 def test_unet_eval_cifar10_golden():
     d = load("ncsnpp_cifar10_eval.npz")
     sd = weights.make_state_dict(O.param_shapes(O.CIFAR10_CFG), seed=int(d["seed"]))
     eng = engine_for(O.CIFAR10_CFG, sd, d["x"].shape[0])
     y = eng.unet_forward(d["x"].cuda(), d["labels"].cuda()).cpu()
-    assert eng.launches_per_eval == 328   # 204 GEMMs (103 with a fused GroupNorm epilogue; the input conv is one of them) + 60 x (gn_finalize + gn_apply) + pad_in, update, embed, attn_small
+    # 159 GEMMs (103 with a fused GroupNorm epilogue; the input conv is one of them) + 9 one-kernel attention blocks (16x16,
+    # each replaces five GEMM launches) + 60 x (gn_finalize + gn_apply) + pad_in, update, embed, attn_small
+    assert eng.launches_per_eval == 292
     assert eng.fused_gn_gemms == 103    # 76 x GroupNorm_1 (resident accumulators) + 27 x the next block's GroupNorm_0 (late; 3x3 convs at <= 16x16)
     eng.close()
     assert rel(y, d["y"]) < TOL_EVAL, rel(y, d["y"])

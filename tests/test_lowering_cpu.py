@@ -12,6 +12,7 @@ CASES = [
     ("small-attn", O.tiny_cfg(64, (1, 2), 1, (8,), 16), 3),
     ("tc-attn", O.tiny_cfg(64, (1, 2, 2), 1, (16,), 32), 2),
     ("odd-batch", O.tiny_cfg(64, (1, 2), 2, (4,), 8), 5),
+    ("fused-attn-block", O.tiny_cfg(128, (1, 2), 1, (16,), 32), 2),   # T = 256 tokens x C = 256: the one-kernel attention block
 ]
 
 
@@ -27,6 +28,15 @@ def test_lowering_matches_oracle(name, cfg, B):
     assert ((y32 - y).norm() / y.norm()).item() < 1e-5
     y16 = Interp(prog, emulate_bf16=True).run(x, t)
     assert ((y16 - y).norm() / y.norm()).item() < 2e-2
+    kinds = [op.kind for op in prog.ops]
+    if name == "fused-attn-block":
+        assert kinds.count("attn_block") == 3 and not any(op.kind == "gemm" and op.args["softmax"] for op in prog.ops)
+        unfused = L.lower(cfg, sd, B, fuse_attn=False)
+        assert [op.kind for op in unfused.ops].count("attn_block") == 0 and len(unfused.ops) > len(prog.ops)
+        yu = Interp(unfused, emulate_bf16=False).run(x, t)
+        assert ((yu - y32).norm() / y.norm()).item() < 1e-5
+    else:
+        assert "attn_block" not in kinds
 
 
 def test_param_shapes_match_oracle_and_count():
