@@ -19,8 +19,10 @@
 //   G5  T0 = P . v            (A = X, B = Z)
 //   D5  X  = bf16(T0 / rowsum)                                         (after G5)
 //   G6  T1 = o . W3^T         (A = X, B = Y)
-//   E   out = (T1 + b3 + x) alpha, fp32, + per-channel partial statistics (staging aliases Z); the next sample's
-//       h / Wv loads and G1 run underneath it
+//   TMA      Wq of the NEXT sample -> Z          (after G5)
+//   E   out = (T1 + b3 + x) alpha, fp32, + per-channel partial statistics; the next sample's h / Wv loads and G1 run
+//       underneath it. x was pulled into L2 at the start of the sample (cp.async.bulk.prefetch.L2): all CTA pairs reach E at
+//       about the same time, and with x coming from HBM there E took 38 % of the kernel (ncu) while HBM idled elsewhere.
 //
 // Warp roles as in dp_gemm.cu: warp 0 = TMA producer (one lane, both CTAs), warp 1 = MMA issuer (leader CTA only),
 // warp 2 = TMEM allocator, warps 4-11 = the eight drain / epilogue warps (two per TMEM lane quadrant, 128 columns each).
@@ -38,13 +40,13 @@ constexpr int kBufBytes = 128 * 256 * 2;    // one operand buffer: 4 K-chunks
 constexpr int kChunkBytes = 128 * 64 * 2;   // [128 rows][64 bf16]
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
-constexpr int kStgPitch = 36;               // floats per staged row (see dp_gemm.cu)
+constexpr int kStgPitch = 36;               // floats per staged row: 32 columns + 4 (conflict-free 128-bit accesses)
 constexpr int kBiasFloats = 4 * 256;
 constexpr int kStatFloats = 4 * 256 * 2;    // [4 lane quadrants][256 channels][sum | sumsq]
 constexpr int kRedFloats = 2 * 2 * 128;     // [max | sum][column half][row]
+constexpr int kStgFloats = kEpiWarps * 16 * kStgPitch;   // transposing staging of the output epilogue: 16 rows x 32 columns per warp
 constexpr int kBarBytes = 256;
-constexpr size_t kSmemBytes = 3 * kBufBytes + (kBiasFloats + kStatFloats + kRedFloats) * 4 + kBarBytes;
-static_assert(kEpiWarps * 32 * kStgPitch * 4 <= kBufBytes, "the epilogue staging aliases one operand buffer");
+constexpr size_t kSmemBytes = 3 * kBufBytes + (kBiasFloats + kStatFloats + kRedFloats + kStgFloats) * 4 + kBarBytes;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier map (8 bytes each)
@@ -52,11 +54,14 @@ constexpr int BAR_LD = 0;      // 5: h, Wv, Wq, Wk, W3 landed (leader CTA's barr
 constexpr int BAR_G = 5;       // 6: GEMM i complete (tcgen05.commit multicast to both CTAs)
 constexpr int BAR_D = 11;      // 4: drains D1, D2+D3, D4, D5 complete (leader's barriers, 16 warp arrivals)
 constexpr int BAR_E = 15;      // epilogue done with T1 (leader's barrier, 16 warp arrivals)
-constexpr int BAR_EL = 16;     // epilogue done with the staging in Z (own CTA, 8 warp arrivals)
 constexpr int BAR_HOLDER = 20; // TMEM base address
 
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pulls [p, p + bytes) into L2 (no destination: the later loads of the epilogue hit there)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -87,7 +92,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   float* const sbias = reinterpret_cast<float*>(smem_raw + 3 * kBufBytes);
   float* const sstats = sbias + kBiasFloats;
   float* const sred = sstats + kStatFloats;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(sred + kRedFloats);
+  float* const staging = sred + kRedFloats;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(staging + kStgFloats);
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + BAR_HOLDER);
@@ -104,7 +110,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     for (int i = 0; i < 6; ++i) mbar_init(bar(BAR_G + i), 1);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_D + i), 2 * kEpiWarps);
     mbar_init(bar(BAR_E), 2 * kEpiWarps);
-    mbar_init(bar(BAR_EL), kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_holder)), 512);
@@ -128,18 +133,30 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) tma_load_2d_pair(dst + kc * kChunkBytes, map, sig, kc * 64, row);
       };
+      // this CTA's 128 rows of x (one contiguous 128 KiB block) on their way into L2 ahead of the output epilogue
+      auto prefetch_x = [&](int s) {
+        const char* xr = reinterpret_cast<const char*>(p.resid) +
+                         (static_cast<size_t>(s) * kAttnBlockT + rank * 128) * kAttnBlockC * sizeof(float);
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) prefetch_l2_bulk(xr + i * 16384, 16384);
+      };
       int n = 0;
+      if (pair < p.B) load(Z, &p.tmap_w, 2, 0 * 256 + rank * 128);   // Wq of the first sample
       for (int s = pair; s < p.B; s += npairs, ++n) {
         const uint32_t ph = n & 1, pph = ph ^ 1u;
         if (n > 0) mbar_wait(bar(BAR_G + 5), pph);            // G6 of the previous sample: X and Y are free
         load(X, &p.tmap_h, 0, s * kAttnBlockT + rank * 128);
         load(Y, &p.tmap_w, 1, 2 * 256 + rank * 128);          // Wv
-        if (n > 0) mbar_wait(bar(BAR_EL), pph);               // the previous epilogue's staging (Z)
-        load(Z, &p.tmap_w, 2, 0 * 256 + rank * 128);          // Wq
+        if (p.x_prefetch == 1) prefetch_x(s);
         mbar_wait(bar(BAR_G + 0), ph);                        // G1 read Wv
         load(Y, &p.tmap_w, 3, 1 * 256 + rank * 128);          // Wk
         mbar_wait(bar(BAR_G + 3), ph);                        // G4 read k
         load(Y, &p.tmap_w, 4, 3 * 256 + rank * 128);          // W3
+        if (p.x_prefetch == 2) prefetch_x(s);
+        if (s + npairs < p.B) {
+          mbar_wait(bar(BAR_G + 4), ph);                      // G5 read v^T: Z is free for the next sample's Wq
+          load(Z, &p.tmap_w, 2, 0 * 256 + rank * 128);
+        }
       }
     }
   } else if (warp == 1 && rank == 0) {
@@ -188,9 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     const int te = (warp - 4) * 32 + lane;
     for (int i = te; i < kBiasFloats; i += 32 * kEpiWarps) sbias[i] = __ldg(p.bias + i);
     named_bar(1, 32 * kEpiWarps);
-    float* const stg = reinterpret_cast<float*>(Zp) + (warp - 4) * (32 * kStgPitch);
-    const int c4 = (lane & 7) * 4;
-    const int rsub = lane >> 3;
+    float* const stg = staging + (warp - 4) * (16 * kStgPitch);
+    const int c4 = (lane & 7) * 4;       // epilogue: 32 columns at a time, this thread's 4 of them ...
+    const int rsub = lane >> 3;          // ... in rows rsub, rsub + 4, ..., rsub + 28 of the warp's 32
     const float alpha = p.alpha;
     const uint32_t arrive_leader[5] = {mapa_u32(bar(BAR_D + 0), 0), mapa_u32(bar(BAR_D + 1), 0), mapa_u32(bar(BAR_D + 2), 0),
                                        mapa_u32(bar(BAR_D + 3), 0), mapa_u32(bar(BAR_E), 0)};
@@ -310,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         struct Pre {
           float4 rs[8];
         };
-        auto prefetch = [&](Pre& f, int blk) {
+        auto prefetch = [&](Pre& f, int blk) {   // the residual of one 32-column block: rows rsub + 4 i8
           const int cc = hlf * 128 + blk * 32 + c4;
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8)
@@ -330,30 +347,37 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(arrive_leader[4]);
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * j) =
-                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                            __uint_as_float(r[4 * j + 3]));
-          __syncwarp();
           const float4 b3 = *reinterpret_cast<const float4*>(sbias + 3 * 256 + cc);
           float st[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) st[i] = 0.f;
-          float4 vv[8];
+          // the transposing staging holds 16 rows (the shared-memory budget): rows 0-15 of the warp, then rows 16-31
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) vv[i8] = *reinterpret_cast<const float4*>(stg + (i8 * 4 + rsub) * kStgPitch + c4);
+          for (int hf = 0; hf < 2; ++hf) {
+            if ((lane >> 4) == hf) {
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            float4 v = vv[i8];
-            const float4 rs = cur.rs[i8];
-            v.x = (v.x + b3.x + rs.x) * alpha;
-            v.y = (v.y + b3.y + rs.y) * alpha;
-            v.z = (v.z + b3.z + rs.z) * alpha;
-            v.w = (v.w + b3.w + rs.w) * alpha;
-            *reinterpret_cast<float4*>(outf + (i8 * 4 + rsub) * kAttnBlockC + cc) = v;
-            st[0] += v.x; st[1] += v.y; st[2] += v.z; st[3] += v.w;
-            st[4] += v.x * v.x; st[5] += v.y * v.y; st[6] += v.z * v.z; st[7] += v.w * v.w;
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + (lane & 15) * kStgPitch + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+            }
+            __syncwarp();
+            float4 vv[4];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) vv[i4] = *reinterpret_cast<const float4*>(stg + (i4 * 4 + rsub) * kStgPitch + c4);
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              float4 v = vv[i4];
+              const float4 rs = cur.rs[hf * 4 + i4];
+              v.x = (v.x + b3.x + rs.x) * alpha;
+              v.y = (v.y + b3.y + rs.y) * alpha;
+              v.z = (v.z + b3.z + rs.z) * alpha;
+              v.w = (v.w + b3.w + rs.w) * alpha;
+              *reinterpret_cast<float4*>(outf + (hf * 16 + i4 * 4 + rsub) * kAttnBlockC + cc) = v;
+              st[0] += v.x; st[1] += v.y; st[2] += v.z; st[3] += v.w;
+              st[4] += v.x * v.x; st[5] += v.y * v.y; st[6] += v.z * v.z; st[7] += v.w * v.w;
+            }
+            __syncwarp();
           }
           // fold the 4 row groups (lanes l, l+8, l+16, l+24) in a fixed order
 #pragma unroll
@@ -369,10 +393,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
               d[1] = st[4 + u];
             }
           }
-          __syncwarp();
           if (blk + 1 < 4) cur = nxt;
         }
-        if (lane == 0) mbar_arrive(bar(BAR_EL));   // the staging in Z has been read: Wq of the next sample may land
         named_bar(1, 32 * kEpiWarps);
         if (p.stats != nullptr) {                  // the four lane quadrants in a fixed order: deterministic partial sums
           float sm = 0.f, sq = 0.f;

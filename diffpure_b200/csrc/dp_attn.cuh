@@ -24,6 +24,7 @@ struct AttnBlockParams {
   int B;
   float scale;         // C^-1/2, folded into q
   float alpha;         // 1/sqrt(2) (skip_rescale) or 1
+  int x_prefetch;      // when x is pulled into L2 ahead of the output epilogue: 0 never, 1 at the start of the sample, 2 after G4
 };
 
 constexpr int kAttnBlockT = 256;

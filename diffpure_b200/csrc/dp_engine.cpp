@@ -783,6 +783,7 @@ int dp_op_attn_block(dp_engine* e, const dp_attn_block_desc* d) {
   a.B = d->B;
   a.scale = d->scale;
   a.alpha = d->alpha;
+  a.x_prefetch = [] { const char* v = std::getenv("DP_ATTN_XPF"); return v ? std::atoi(v) : 2; }();
   e->ops.push_back(op);
   return DP_OK;
 }

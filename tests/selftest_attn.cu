@@ -81,6 +81,7 @@ static void make(Data& d, int B, float wscale) {
   d.p.B = B;
   d.p.scale = 1.0f / 16.0f;
   d.p.alpha = 0.70710678f;
+  d.p.x_prefetch = getenv("DP_ATTN_XPF") ? atoi(getenv("DP_ATTN_XPF")) : 2;
 }
 
 static void release(Data& d) {

@@ -87,6 +87,19 @@ def captures():
                f"python tests/gpu_profile_eval.py 512 1  ({tag})", f"{tag}_gemm_ncu_full.txt",
                "# the first res-blocks of one DDPM++ evaluation at B=512: gemm_kernel<128, 8192 (E_GN), 2> = a 128->128 @32x32 conv with a fused\n"
                "# GroupNorm epilogue, gemm_kernel<128, 849, 2> = Conv_1 128->128 @32x32 (+bias, fp32 residual, 1/sqrt2, fp32 out, statistics); CTA pairs")
+    resb = dump(f"prof_{tag}b_gemm.ncu-rep",
+                f"the same command with the row-patch mainloop (final {tag} code): ncu --set full --clock-control none --import-source on "
+                f"-k regex:gemm_kernel -s 4 -c 6 python tests/gpu_profile_eval.py 512 1", f"{tag}_gemm_patch_ncu_full.txt",
+                "# gemm_kernel<128, 8192 (E_GN), 2> = 128->128 @32x32 conv, fused GroupNorm epilogue; <128, 849, 2> = Conv_1 (+ fp32 residual);\n"
+                "# compare l1tex__m_xbar2l1tex_read_bytes (L2 -> SM bytes) and the duration with the tile-per-tap capture in "
+                f"{tag}_gemm_ncu_full.txt")
+    res = resb or res
+    dump(f"prof_{tag}_adm.ncu-rep",
+         f"ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 4 -c 2 python tests/gpu_fullsize_256.py adm 32 ({tag})",
+         f"{tag}_adm_conv_ncu.txt", "# ImageNet ADM (guided_diffusion 256x256 unconditional) at B=32: the first 256x256-resolution conv launches (CTA pairs)")
+    dump("prof_attn.ncu-rep",
+         f"ncu --set full --clock-control none --import-source on -k regex:attn_block -s 2 -c 1 ./diffpure_b200/selftest_attn perf 512 ({tag})",
+         f"{tag}_attn_block_ncu.txt", "# dp::attn_block_kernel: the whole AttnBlockpp behind its GroupNorm for 512 samples of 256 tokens x 256 channels")
     if res:
         h, u, rows = res
         idx = {k: i for i, k in enumerate(h)}
@@ -95,7 +108,7 @@ def captures():
               for r in rows if "849" in r[idx["Kernel Name"]]]
         if tr:
             json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "launches": len(tr),
-                       "source": f"profiles/{tag}_gemm_ncu_full.txt (Conv_1 128->128 @32x32 launches, dram__bytes_read.sum + dram__bytes_write.sum)",
+                       "source": f"profiles/{tag}_gemm{'_patch' if resb else ''}_ncu_full.txt (Conv_1 128->128 @32x32 launches, dram__bytes_read.sum + dram__bytes_write.sum)",
                        "algorithmic_bytes_per_launch_note": "B=512 conv 128->128 @32x32 with fp32 residual: A bf16 134 MB + residual 268 MB + out 268 MB "
                                                             "= 671 MB algorithmic (part of the output is still in L2 at kernel end)"},
                       open(os.path.join(out, "gemm_dram_bytes_per_launch.json"), "w"), indent=1)
