@@ -63,6 +63,11 @@ __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_add
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// the same for one TMA box of a tensor map
+__device__ __forceinline__ void prefetch_l2_box(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -152,8 +157,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         load(Y, &p.tmap_w, 3, 1 * 256 + rank * 128);          // Wk
         mbar_wait(bar(BAR_G + 3), ph);                        // G4 read k
         load(Y, &p.tmap_w, 4, 3 * 256 + rank * 128);          // W3
-        if (p.x_prefetch == 2) prefetch_x(s);
+        if (p.x_prefetch >= 2) prefetch_x(s);
         if (s + npairs < p.B) {
+          if (p.x_prefetch == 3) {   // the next sample's h rows as well: their TMA load is issued the moment G6 retires
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) prefetch_l2_box(&p.tmap_h, kc * 64, (s + npairs) * kAttnBlockT + rank * 128);
+          }
           mbar_wait(bar(BAR_G + 4), ph);                      // G5 read v^T: Z is free for the next sample's Wq
           load(Z, &p.tmap_w, 2, 0 * 256 + rank * 128);
         }

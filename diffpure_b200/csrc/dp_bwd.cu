@@ -91,6 +91,16 @@ __device__ __forceinline__ float load_x(const GnBwdParams& p, int b, int pix, in
   return __ldg(p.src1 + (static_cast<size_t>(b) * HW + pix) * p.C1 + (c - p.C0));
 }
 
+// FiLM / scale-shift norm (guided_diffusion unet.py:255-258: h = norm(h) * (1 + scale) + shift, then SiLU): for the input
+// gradient the per-sample scale and shift just replace gamma, beta by gamma (1 + scale), beta (1 + scale) + shift.
+__device__ __forceinline__ void film_fold(const GnBwdParams& p, int b, int c, int C, float& gam, float& bet) {
+  if (p.film == nullptr) return;
+  const float sc = 1.0f + __ldg(p.film + static_cast<size_t>(b) * p.film_ld + c);
+  const float sh = __ldg(p.film + static_cast<size_t>(b) * p.film_ld + C + c);
+  bet = bet * sc + sh;
+  gam = gam * sc;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -115,8 +125,9 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(GnBwdParams p) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const float mean = gs[2 * g], rstd = gs[2 * g + 1];
-    const float gam = __ldg(p.gamma + c);
-    const float bet = p.silu ? __ldg(p.beta + c) : 0.f;
+    float gam = __ldg(p.gamma + c);
+    float bet = p.silu ? __ldg(p.beta + c) : 0.f;
+    film_fold(p, b, c, C, gam, bet);
     float s1 = 0.f, s2 = 0.f;
     for (int pix = px0; pix < px1; ++pix) {
       const int h = pix / p.W, w = pix - h * p.W;
@@ -171,8 +182,9 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdParams p) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const float mean = gs[2 * g], rstd = gs[2 * g + 1], m1 = gm[2 * g], m2 = gm[2 * g + 1];
-    const float gam = __ldg(p.gamma + c);
-    const float bet = p.silu ? __ldg(p.beta + c) : 0.f;
+    float gam = __ldg(p.gamma + c);
+    float bet = p.silu ? __ldg(p.beta + c) : 0.f;
+    film_fold(p, b, c, C, gam, bet);
     for (int pix = px0; pix < px1; ++pix) {
       const int h = pix / p.W, w = pix - h * p.W;
       const float xhat = (load_x(p, b, pix, c) - mean) * rstd;
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float inv = 1.0f / rowsum[row];
+  const float inv = rowsum != nullptr ? 1.0f / rowsum[row] : 1.0f;   // no row sums: pnum is already normalised
   const __nv_bfloat16* pr = pnum + row * T;
   const float* dr = dp_ + row * T;
   float dot = 0.f;

@@ -102,6 +102,7 @@ struct GnBwdParams {
   const float* src0; const __nv_bfloat16* src0h; const float* stats0; int C0, P0;
   const float* src1; const float* stats1; int C1, P1;
   const float* gamma; const float* beta;
+  const float* film; int film_ld;       // optional per-sample [scale | shift] rows (scale-shift norm), as GnParams.film
   int B, H, W, groups; float eps; int silu; int resample;
   const float* g;
   const float* add0; float add0_scale;  // optional fp32 at the output resolution, C0+C1 channels: d += scale * resample^T(add0)

@@ -815,6 +815,8 @@ int dp_op_gn_bwd(dp_engine* e, const dp_gn_bwd_desc* d) {
   p.stats0 = d->stats0; p.C0 = d->C0; p.P0 = d->P0;
   p.src1 = d->src1; p.stats1 = d->stats1; p.C1 = d->C1; p.P1 = d->P1;
   p.gamma = d->gamma; p.beta = d->beta;
+  p.film = d->film; p.film_ld = d->film_ld;
+  if (d->film && (d->C1 || !d->silu)) return fail(e, DP_ERR_INVALID, "gn_bwd: scale-shift rows go with a single source and SiLU");
   p.B = d->B; p.H = d->H; p.W = d->W; p.groups = d->groups; p.eps = d->eps; p.silu = d->silu; p.resample = d->resample;
   p.g = d->g; p.add0 = d->add0; p.add0_scale = d->add0_scale; p.add1 = d->add1;
   p.d0_f32 = d->d0_f32; p.d0_bf16 = static_cast<__nv_bfloat16*>(d->d0_bf16); p.d1_f32 = d->d1_f32;

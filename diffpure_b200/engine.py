@@ -230,7 +230,8 @@ class Engine:
                                    self._p(a["stats1"]), a["C1"], a["P1"], self._p(a["gamma"]), self._p(a["beta"]),
                                    a["B"], a["H"], a["W"], a["groups"], a["eps"], a["silu"], a["resample"],
                                    self._p(a["g"]), self._p(a["add0"]), a["add0_scale"], self._p(a["add1"]),
-                                   self._p(a["d0_f32"]), self._p(a["d0_bf16"]), self._p(a["d1_f32"]))
+                                   self._p(a["d0_f32"]), self._p(a["d0_bf16"]), self._p(a["d1_f32"]),
+                                   self._p(a.get("film")), a.get("film_ld", 0))
                 self._check(L.dp_op_gn_bwd(self.h, C.byref(d)), "dp_op_gn_bwd")
             elif op.kind == "softmax_bwd":
                 d = _lib.SoftmaxBwdDesc(self._p(a["pnum"]), self._p(a["rowsum"]), self._p(a["dp"]), self._p(a["ds"]),

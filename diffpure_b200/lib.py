@@ -74,7 +74,7 @@ class GnBwdDesc(C.Structure):
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int), ("eps", C.c_float),
                 ("silu", C.c_int), ("resample", C.c_int), ("g", C.c_void_p), ("add0", C.c_void_p),
                 ("add0_scale", C.c_float), ("add1", C.c_void_p), ("d0_f32", C.c_void_p), ("d0_bf16", C.c_void_p),
-                ("d1_f32", C.c_void_p)]
+                ("d1_f32", C.c_void_p), ("film", C.c_void_p), ("film_ld", C.c_int)]
 
 
 class SoftmaxBwdDesc(C.Structure):

@@ -64,7 +64,7 @@ def act_seg(t, C, taps=1, stride=1, c_total=None, offset=0):
     return ASeg(view(t, offset), C, C if c_total is None else c_total, taps, stride, 1 if (taps == 9 and stride == 1) else 0)
 
 
-def lower_attention(prog, name, hn, wq, wk, wv, bq, bk, bv, B, T, C, heads, scale):
+def lower_attention(prog, name, hn, wq, wk, wv, bq, bk, bv, B, T, C, heads, scale, rec=None):
     """Self-attention core on a normalised bf16 input hn [B*T, C]: returns o bf16 [B*T, C] with channel h*d + c.
 
     wq/wk/wv: [C, C] (out, in) with output rows ordered head-major; b*: [C].
@@ -81,6 +81,8 @@ def lower_attention(prog, name, hn, wq, wk, wv, bq, bk, bv, B, T, C, heads, scal
         prog.gemm([act_seg(hn, C)], prog.const_bf16(name + ".wqkv", torch.cat([wq, wk, wv], 0)), 3 * C, C, 1, 1, B * T,
                   3 * C, bias=prog.const_f32(name + ".bqkv", torch.cat([bq, bk, bv])), out_bf16=qkv)
         prog.attn_small(qkv, o, B, T, heads, d, scale)
+        if rec is not None:
+            rec.update(qkv=qkv)
         return o
     assert T % 128 == 0 and d % 64 == 0, "tensor-core attention needs T % 128 == 0 and head dim % 64 == 0"
     qk = prog.tensor(name + ".qk", B * T * 2 * C, "bf16")
@@ -107,4 +109,56 @@ def lower_attention(prog, name, hn, wq, wk, wv, bq, bk, bv, B, T, C, heads, scal
     prog.gemm([act_seg(pm, T)], vt, B * C, T, 1, 1, T, d, batch=B * heads, inner=heads, a_batch_rows=heads * T,
               a_inner_rows=T, b_batch_rows=C, b_inner_rows=d, out_batch_stride=T * C, out_inner_stride=d, rowscale=rs,
               out_bf16=o, ldc=C)
+    if rec is not None:      # what the data-gradient of this block reads (lower_attention_bwd)
+        rec.update(qk=qk, vt=vt, pm=pm, rs=rs)
     return o
+
+
+def pack_dgrad3x3(w):
+    """Conv2d weight [Cout, Cin, 3, 3] -> the B operand of its data-gradient GEMM (the same implicit 3x3 GEMM with the
+    taps flipped and in / out swapped): [Cin, 9*Cout] with K index = (ky*3+kx)*Cout + co reading w[co, ci, 2-ky, 2-kx]."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous()
+
+
+def transposed(prog, name, src, rows, cols, ld_in, in_batch_stride, batch):
+    """bf16 [batch][rows][cols] (row pitch ld_in) -> new tensor [batch][cols][rows]."""
+    out = prog.tensor(name, batch * rows * cols, "bf16")
+    prog.transpose(src, out, rows, cols, ld_in, rows, batch, in_batch_stride, rows * cols)
+    return out
+
+
+def lower_attention_bwd(prog, name, rec, go, B, T, C, heads, scale):
+    """Data-gradient of `lower_attention`: go = dL/d(o) bf16 [B*T, C] -> dq | dk | dv bf16 [B*T, 3C] (head-major columns
+    inside each third, as the forward q | k | v). Per (sample, head): dV = P^T dO, dP = dO V^T, dS = P (dP - rowsum(dP P)),
+    dQ = scale dS K, dK = scale dS^T Q -- tcgen05 GEMMs over bf16 transposes + the row-wise `softmax_bwd` kernel
+    (`attn_small_bwd` for T <= 64)."""
+    from .program import view
+    d = C // heads
+    dqkv = prog.tensor(name + ".dqkv", B * T * 3 * C, "bf16")
+    if T <= 64:
+        prog.attn_small_bwd(rec["qkv"], go, dqkv, B, T, heads, d, scale)
+        return dqkv
+    qk, vt, pm, rs = rec["qk"], rec["vt"], rec["pm"], rec["rs"]
+    v = transposed(prog, name + ".v", vt, C, T, T, C * T, B)                          # [B][T][C]
+    qT = transposed(prog, name + ".qT", view(qk, 0), T, C, 2 * C, T * 2 * C, B)       # [B][C][T]
+    kT = transposed(prog, name + ".kT", view(qk, C), T, C, 2 * C, T * 2 * C, B)
+    goT = transposed(prog, name + ".goT", go, T, C, C, T * C, B)
+    BH = B * heads
+    # dP[b,h] = dO[b,:,h] . V[b,:,h]^T   (fp32 [B][heads][T][T])
+    dp = prog.tensor(name + ".dp", BH * T * T, "f32")
+    prog.gemm([act_seg(go, d, c_total=C)], v, B * T, C, 1, 1, T, T, batch=BH, inner=heads, a_batch_rows=T, a_inner_k=d,
+              b_batch_rows=T, b_inner_k=d, w_cols=C, out_batch_stride=heads * T * T, out_inner_stride=T * T, out_f32=dp,
+              ldc=T)
+    ds = prog.tensor(name + ".ds", BH * T * T, "bf16")
+    pn = prog.tensor(name + ".pn", BH * T * T, "bf16")
+    prog.softmax_bwd(pm, rs, dp, ds, pn, BH * T, T)            # rs None: pm is the normalised softmax already
+    dsT = transposed(prog, name + ".dsT", ds, T, T, T, T * T, BH)
+    pnT = transposed(prog, name + ".pnT", pn, T, T, T, T * T, BH)
+    # [T, d] results into the head's columns of the q / k / v third of dqkv
+    bat = dict(batch=BH, inner=heads, a_batch_rows=heads * T, a_inner_rows=T, b_batch_rows=C, b_inner_rows=d,
+               out_batch_stride=T * 3 * C, out_inner_stride=d, ldc=3 * C)
+    prog.gemm([act_seg(ds, T)], kT, B * C, T, 1, 1, T, d, alpha=scale, out_bf16=view(dqkv, 0), **bat)
+    prog.gemm([act_seg(dsT, T)], qT, B * C, T, 1, 1, T, d, alpha=scale, out_bf16=view(dqkv, C), **bat)
+    prog.gemm([act_seg(pnT, T)], goT, B * C, T, 1, 1, T, d, out_bf16=view(dqkv, 2 * C), **bat)
+    return dqkv

@@ -18,7 +18,8 @@ from types import SimpleNamespace
 
 import torch
 
-from .lowering_common import INV_SQRT2, Act, act_seg, new_act, pack_conv1x1, pack_conv3x3, pack_conv_in, pad_rows
+from .lowering_common import INV_SQRT2, Act, act_seg, new_act, pack_conv1x1, pack_conv3x3, pack_conv_in, pack_dgrad3x3, \
+    pad_rows, transposed as _transposed
 from .program import Program, view
 
 
@@ -363,13 +364,6 @@ def lower(cfg, sd, B, h_bf16=True, tape=None, fuse_gn=True, fuse_attn=True):
     return prog
 
 
-def pack_dgrad3x3(w):
-    """Data gradient of a 'same' 3x3 conv = the same conv with the taps flipped and in/out swapped:
-    [Cout, Cin, 3, 3] -> [Cin, 9*Cout] with K index = (ky*3+kx)*Cout + co reading w[co, ci, 2-ky, 2-kx]."""
-    co, ci = w.shape[0], w.shape[1]
-    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous()
-
-
 def lower_vjp(cfg, sd, B):
     """Forward (with a tape) followed by the data-gradient ops: the program of `dp_unet_vjp`, gx = J(x, t)^T g.
 
@@ -495,10 +489,3 @@ def lower_vjp(cfg, sd, B):
     prog.update(gx8, 8, B, S, S, ncol)
     prog.meta.update(vjp=True)
     return prog
-
-
-def _transposed(prog, name, src, rows, cols, ld_in, in_batch_stride, B):
-    """bf16 [B][rows][cols] (row pitch ld_in) -> new tensor [B][cols][rows]."""
-    out = prog.tensor(name, B * rows * cols, "bf16")
-    prog.transpose(src, out, rows, cols, ld_in, rows, B, in_batch_stride, rows * cols)
-    return out

@@ -147,8 +147,9 @@ class Program:
 
     # -- data-gradient ops (input gradient of the network; diffpure_b200/csrc/dp_bwd.cu) -------------------
     def gn_bwd(self, *, src0, stats0, C0, P0, gamma, beta, B, H, W, groups, eps, silu, g, src1=None, stats1=None, C1=0,
-               P1=0, resample=0, add0=None, add0_scale=1.0, add1=None, d0_f32=None, d0_bf16=None, d1_f32=None):
-        self.add("gn_bwd", src0=view(src0), stats0=view(stats0), C0=C0, P0=P0, src1=view(src1), stats1=view(stats1),
+               P1=0, resample=0, add0=None, add0_scale=1.0, add1=None, d0_f32=None, d0_bf16=None, d1_f32=None,
+               film=None, film_ld=0):
+        self.add("gn_bwd", film=view(film), film_ld=film_ld, src0=view(src0), stats0=view(stats0), C0=C0, P0=P0, src1=view(src1), stats1=view(stats1),
                  C1=C1, P1=P1, gamma=view(gamma), beta=view(beta), B=B, H=H, W=W, groups=groups, eps=float(eps),
                  silu=silu, resample=resample, g=view(g), add0=view(add0), add0_scale=float(add0_scale),
                  add1=view(add1), d0_f32=view(d0_f32), d0_bf16=view(d0_bf16), d1_f32=view(d1_f32))

@@ -198,8 +198,8 @@ class PurifyRunner(torch.nn.Module):
             return False
         if getattr(self.model, "_lower_vjp", None) is None and not hasattr(self.model, "vjp_ok"):
             raise NotImplementedError(
-                "diffpure_b200: backward through the purification loop is implemented for the DDPM++ (CIFAR-10) network "
-                "only; wrap the call in torch.no_grad() / detach the input for this network")
+                "diffpure_b200: backward through the purification loop is implemented for the DDPM++ (CIFAR-10) and ADM "
+                "(ImageNet) networks; wrap the call in torch.no_grad() / detach the input for this network")
         return True
 
     def _passes(self, x0, dump, one_pass):

@@ -78,7 +78,8 @@ def build_score_model(config, state_dict=None):
         img_shape = (3, cfg.image_size, cfg.image_size)
         if state_dict is None:
             state_dict = torch.load('pretrained/guided_diffusion/256x256_diffusion_uncond.pt', map_location='cpu')
-        model = ScoreModel("adm", cfg, state_dict, lowering_adm.lower, out_channels=6)
+        model = ScoreModel("adm", cfg, state_dict, lowering_adm.lower, out_channels=6,
+                           lower_vjp_fn=lowering_adm.lower_vjp)
     elif config.data.dataset == 'CIFAR10':
         from .. import lowering_ncsnpp
         cfg = lowering_ncsnpp.cfg_from_reference(config)

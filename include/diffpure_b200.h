@@ -197,9 +197,10 @@ typedef struct {
   const float* add0; float add0_scale; /* optional, output resolution, C0+C1 channels (shortcut branch) */
   const float* add1;                   /* optional, [B,H,W,C0] (gradient that reached src0 through a skip connection) */
   float* d0_f32; void* d0_bf16; float* d1_f32;
+  const float* film; int film_ld;      /* optional scale-shift rows of the forward op (guided_diffusion unet.py:255-258), first source only */
 } dp_gn_bwd_desc;
 
-/* softmax backward per row: P = pnum / rowsum, dS = P (dP - sum_j dP_j P_j); writes dS and P as bf16. */
+/* softmax backward per row: P = pnum / rowsum (rowsum NULL: pnum is P), dS = P (dP - sum_j dP_j P_j); writes dS and P as bf16. */
 typedef struct {
   const void* pnum_bf16; const float* rowsum; const float* dp; void* ds_bf16; void* pn_bf16; long long rows; int T;
 } dp_softmax_bwd_desc;

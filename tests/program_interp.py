@@ -289,7 +289,7 @@ class Interp:
         return t
 
     def op_gn_bwd(self, src0, stats0, C0, P0, src1, stats1, C1, P1, gamma, beta, B, H, W, groups, eps, silu, resample,
-                  g, add0, add0_scale, add1, d0_f32, d0_bf16, d1_f32):
+                  g, add0, add0_scale, add1, d0_f32, d0_bf16, d1_f32, film=None, film_ld=0):
         C = C0 + C1
         HW = H * W
         Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
@@ -309,9 +309,16 @@ class Interp:
         mean = mean.float().repeat_interleave(cpg, 1)[:, None, None, :]
         xhat = (x - mean) * rstd
         gam = self.rd(gamma, (C,))[None, None, None, :]
+        bet = self.rd(beta, (C,))[None, None, None, :]
+        if film is not None:   # scale-shift norm: per-sample (1 + scale), shift fold into gamma, beta
+            fb, fo = self.flat(film)
+            f = torch.as_strided(fb, (B, 2 * C), (film_ld, 1), fo)
+            sc = 1 + f[:, None, None, :C]
+            bet = bet * sc + f[:, None, None, C:]
+            gam = gam * sc
         gy = self._resample_T(self.rd(g, (B, Ho, Wo, C)), resample)
         if silu:
-            u = xhat * gam + self.rd(beta, (C,))[None, None, None, :]
+            u = xhat * gam + bet
             s = torch.sigmoid(u)
             gy = gy * (s * (1 + u * (1 - s)))
         gx = gy * gam
@@ -334,7 +341,9 @@ class Interp:
             self.wr(d1_f32, d[..., C0:], (B, H, W, C1), (HW * C1, W * C1, C1, 1))
 
     def op_softmax_bwd(self, pnum, rowsum, dp, ds, pn, rows, T):
-        P = self.rd(pnum, (rows, T)) / self.rd(rowsum, (rows,))[:, None]
+        P = self.rd(pnum, (rows, T))
+        if rowsum is not None:
+            P = P / self.rd(rowsum, (rows,))[:, None]
         dP = self.rd(dp, (rows, T))
         dS = P * (dP - (dP * P).sum(-1, keepdim=True))
         self.wr(ds, dS, (rows, T), (T, 1))

@@ -93,17 +93,70 @@ def test_runner_gradient_through_a_three_step_loop():
     runner.model.release()
 
 
-def test_adm_gradient_request_fails_loudly():
-    """No input-gradient program exists for the ADM network yet: a requires_grad input must raise, never detach."""
+def _adm_tiny():
+    from oracle import adm as A
+    acfg = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))     # attention at T = 1024, 256 and 64; heads of 64 channels
+    return A, acfg, weights.make_state_dict(A.param_shapes(acfg), seed=5)
+
+
+def test_adm_unet_vjp_vs_autograd():
+    """guided_diffusion UNet (scale-shift norm, resblock up / down, multi-head attention): dp_unet_vjp against
+    torch.autograd through the reference-pinned oracle forward, gradient wrt the eps half of the output."""
+    from diffpure_b200 import lowering_adm as LA
+    from diffpure_b200.engine import Engine
+    A, acfg, sd = _adm_tiny()
+    B = 2
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).requires_grad_(True)
+    t = torch.tensor([37.0, 512.0])
+    go = torch.randn(B, 3, 64, 64, generator=g)
+    (A.forward(acfg, sd, x, t)[:, :3] * go).sum().backward()
+    ref = x.grad
+    eng = Engine(LA.lower_vjp(acfg, sd, B), device=0)
+    got = eng.unet_vjp(x.detach().cuda(), t.cuda(), go.cuda()).cpu()
+    got2 = eng.unet_vjp(x.detach().cuda(), t.cuda(), go.cuda()).cpu()
+    eng.close()
+    r = rel(got, ref)
+    print(f"unet vjp adm-tiny: rel-L2 vs autograd on the oracle = {r:.3e}")
+    assert torch.equal(got, got2)
+    assert r < TOL_VJP, r
+
+
+def test_adm_runner_gradient_through_a_three_step_loop():
+    """The ImageNet white-box path (run_in_rand_inf.sh: RevGuidedDiffusion, score_type guided_diffusion, gradient through
+    sdeint_adjoint): d<w, purified>/dx0 over K = 3 Euler-Maruyama steps vs autograd through the oracle loop."""
     from diffpure_b200.runners.diffpure_sde import RevGuidedDiffusion
     from golden_inputs import ADM_TINY_REF_CONFIG
-    from oracle import adm as A
-    acfg = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
-    sd = weights.make_state_dict(A.param_shapes(acfg), seed=5)
-    args = SimpleNamespace(t=2, rand_t=False, t_delta=15, use_bm=False, score_type="guided_diffusion", sample_step=1,
+    from oracle import sde as OS
+    A, acfg, sd = _adm_tiny()
+    t_star = 3
+    args = SimpleNamespace(t=t_star, rand_t=False, t_delta=15, use_bm=False, score_type="guided_diffusion", sample_step=1,
                            log_dir="/tmp/dp_test_logs", save_images=False)
     config = SimpleNamespace(data=SimpleNamespace(dataset="ImageNet"), model=SimpleNamespace(**ADM_TINY_REF_CONFIG))
-    r = RevGuidedDiffusion(args, config, device=torch.device("cuda:0"), state_dict=sd)
+    runner = RevGuidedDiffusion(args, config, device=torch.device("cuda:0"), state_dict=sd)
+    g = torch.Generator().manual_seed(4)
+    x0 = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    e0 = torch.randn(2, 3, 64, 64, generator=g)
+    z = torch.randn(OS.num_steps(t_star), 2, 3, 64, 64, generator=g)
+    w = torch.randn(2, 3, 64, 64, generator=g)
+    xr = x0.clone().requires_grad_(True)
+    out_ref = OS.purify_sde(lambda xx, tt: A.forward(acfg, sd, xx, tt), xr, t_star, e0, z, score_type="guided_diffusion")
+    (ref,) = torch.autograd.grad((out_ref * w).sum(), xr)
+    xg = x0.cuda().requires_grad_(True)
+    out = runner.image_editing_sample(xg, bs_id=5, tag="g", init_noise=e0.cuda(), step_noise=z.cuda())
+    assert out.requires_grad
+    (gx,) = torch.autograd.grad((out * w.cuda()).sum(), xg)
+    r_out, r_g = rel(out.detach().cpu(), out_ref.detach()), rel(gx.cpu(), ref)
+    print(f"ADM K=3 loop: state rel-L2 {r_out:.3e}, input-gradient rel-L2 {r_g:.3e}")
+    assert r_out < 5e-3 and r_g < TOL_VJP, (r_out, r_g)
+    runner.model.release()
+
+
+def test_gradient_request_fails_loudly_where_no_backward_program_exists():
+    """The DDPM (CelebA-HQ, SDEdit) network has no input-gradient program: a requires_grad input must raise, never detach."""
+    from diffpure_b200.runners._common import PurifyRunner
+    r = PurifyRunner()
+    r.model = SimpleNamespace(_lower_vjp=None)
     with pytest.raises(NotImplementedError):
-        r.image_editing_sample(torch.zeros(2, 3, 64, 64, device="cuda").requires_grad_(True))
-    r.model.release()
+        r._wants_grad(torch.zeros(1, 3, 8, 8, device="cuda").requires_grad_(True))
+    assert r._wants_grad(torch.zeros(1, 3, 8, 8, device="cuda")) is False

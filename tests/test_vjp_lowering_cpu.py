@@ -46,3 +46,29 @@ def test_dgrad_weight_packing():
     cols = cols.reshape(2, 24, 9, 64).permute(0, 2, 1, 3).reshape(2, 9 * 24, 64)
     got = torch.einsum("nk,bkp->bnp", wp, cols).reshape(2, 16, 8, 8)
     assert torch.allclose(got, ref, atol=1e-4)
+
+
+def test_adm_vjp_program_matches_autograd_on_the_oracle():
+    """guided_diffusion UNet (scale-shift norm, resblock up / down, multi-head attention at T = 1024 / 256 / 64): the program of
+    `lowering_adm.lower_vjp` against torch.autograd through oracle/adm.py (pinned to the reference modules), for the
+    gradient wrt the eps half of the output (what the VP-SDE path of runners/diffpure_sde.py:96-122 reads)."""
+    from diffpure_b200 import lowering_adm as LA
+    from oracle import adm as A
+    cfg = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    B = 2
+    sd = weights.make_state_dict(A.param_shapes(cfg), seed=5)
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).requires_grad_(True)
+    t = torch.tensor([37.0, 512.0])
+    go = torch.randn(B, 3, 64, 64, generator=g)
+    (A.forward(cfg, sd, x, t)[:, :3] * go).sum().backward()
+    ref = x.grad
+    prog = LA.lower_vjp(cfg, sd, B)
+    kinds = [o.kind for o in prog.ops]
+    assert {"grad_in", "gn_bwd", "gemm", "update", "attn_small_bwd", "softmax_bwd", "transpose"} <= set(kinds)
+    assert any(o.kind == "gn_bwd" and o.args["film"] is not None for o in prog.ops)            # scale-shift norm
+    assert any(o.kind == "softmax_bwd" and o.args["rowsum"] is None for o in prog.ops)         # T = 1024: normalised P
+    got = Interp(prog, emulate_bf16=False).run_vjp(x.detach(), t, go)
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-4
+    got16 = Interp(prog, emulate_bf16=True).run_vjp(x.detach(), t, go)
+    assert ((got16 - ref).norm() / ref.norm()).item() < 3e-2
