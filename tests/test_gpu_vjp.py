@@ -160,3 +160,25 @@ def test_gradient_request_fails_loudly_where_no_backward_program_exists():
     with pytest.raises(NotImplementedError):
         r._wants_grad(torch.zeros(1, 3, 8, 8, device="cuda").requires_grad_(True))
     assert r._wants_grad(torch.zeros(1, 3, 8, 8, device="cuda")) is False
+
+
+def test_adm_fullsize_unet_vjp_vs_autograd():
+    """The full ImageNet network (256x256, 552.8 M parameters, attention at T = 1024 / 256 / 64 with 4 - 16 heads): dp_unet_vjp
+    at B = 1 against torch.autograd through the oracle forward on the host (random-init weights of the real shapes)."""
+    from diffpure_b200 import lowering_adm as LA, synthetic
+    from diffpure_b200.engine import Engine
+    from oracle import adm as A
+    cfg = LA.imagenet_cfg()
+    sd = synthetic.random_state_dict(LA.param_shapes(cfg), seed=0)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).requires_grad_(True)
+    t = torch.tensor([77.0])
+    go = torch.randn(1, 3, 256, 256, generator=g)
+    (A.forward(A.IMAGENET_CFG, sd, x, t)[:, :3] * go).sum().backward()
+    ref = x.grad
+    eng = Engine(LA.lower_vjp(cfg, sd, 1), device=0)
+    got = eng.unet_vjp(x.detach().cuda(), t.cuda(), go.cuda()).cpu()
+    eng.close()
+    r = rel(got, ref)
+    print(f"unet vjp adm-full (256x256, B=1): rel-L2 vs autograd on the oracle = {r:.3e}")
+    assert r < TOL_VJP, r
