@@ -19,30 +19,29 @@ class GuidedDiffusion(PurifyRunner):
         super().__init__()
         self._setup(args, config, device)
         cfg = lowering_adm.cfg_from_reference(config)
-        # The reference builds a SpacedDiffusion from these fields (script_util.py:82-132, respace.py:71-99); this runner
-        # implements the configuration DiffPure ships (configs/imagenet.yml: full 1000-step linear chain, rescaled
-        # timesteps) and refuses anything else instead of silently running a different chain.
+        # The reference builds a SpacedDiffusion from these fields (script_util.py:82-132, respace.py:63-99); the same chain
+        # is rebuilt here as host tables (schedule.GuidedChain) -- configs/imagenet.yml ships the full 1000-step linear
+        # chain with rescaled timesteps, and invites changing timestep_respacing.
         m = config.model
-        n_steps = int(getattr(m, "diffusion_steps", 1000))
-        if str(getattr(m, "timestep_respacing", "") or "") not in ("", str(n_steps)):
-            raise NotImplementedError(f"timestep_respacing={m.timestep_respacing!r} is not supported (only the full chain)")
-        if getattr(m, "noise_schedule", "linear") != "linear":
-            raise NotImplementedError(f"noise_schedule={m.noise_schedule!r} is not supported (only 'linear')")
-        if not getattr(m, "rescale_timesteps", True):
-            raise NotImplementedError("rescale_timesteps=False is not supported")
+        self._chain_kw = dict(n=int(getattr(m, "diffusion_steps", 1000)),
+                              noise_schedule=getattr(m, "noise_schedule", "linear"),
+                              timestep_respacing=str(getattr(m, "timestep_respacing", "") or ""),
+                              rescale_timesteps=bool(getattr(m, "rescale_timesteps", True)))
+        chain = schedule.GuidedChain(**self._chain_kw)
         if state_dict is None:
             state_dict = torch.load(f'{model_dir}/256x256_diffusion_uncond.pt', map_location='cpu')
         self.model = ScoreModel("adm", cfg, state_dict, lowering_adm.lower, out_channels=6).eval()
-        self.num_timesteps = int(getattr(config.model, "diffusion_steps", 1000))
-        base = schedule._linear_betas64(self.num_timesteps)
-        self.diffusion = SimpleNamespace(betas=base, num_timesteps=self.num_timesteps)
-        self.betas = torch.from_numpy(base).float().to(self.device)
+        self.num_timesteps = chain.num_timesteps
+        self.diffusion = SimpleNamespace(betas=chain.betas, num_timesteps=chain.num_timesteps,
+                                         timestep_map=chain.timestep_map.tolist(),
+                                         rescale_timesteps=chain.rescale, original_num_steps=chain.n_base)
+        self.betas = torch.from_numpy(chain.betas).float().to(self.device)
 
     def image_editing_sample(self, img, bs_id=0, tag=None, init_noise=None, step_noise=None, seed=None):
         with torch.no_grad():
             x0, dev, dump = self._open(img, bs_id, tag)
             eng = self.model.engine_for(x0.shape[0], dev)
-            cond, coef, sx, se = schedule.guided_tables(self.args.t, self.num_timesteps)
+            cond, coef, sx, se = schedule.guided_tables(self.args.t, **self._chain_kw)
 
             def one_pass(it, x):
                 e = self._init_noise(x, init_noise, dev)

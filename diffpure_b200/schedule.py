@@ -60,31 +60,90 @@ def _linear_betas64(n, beta_start=None, beta_end=None):
     return np.linspace(beta_start, beta_end, n, dtype=np.float64)
 
 
-def guided_tables(t_levels, n=1000):
-    """Learned-range p_sample of guided_diffusion for timesteps t_levels-1 ... 0
-    (runners/diffpure_guided.py:59-75; gaussian_diffusion.py:119-180,240-334,403-447; respace.py:71-99 with
-    timestep_respacing '1000', i.e. betas re-derived from the cumulative products; rescale_timesteps -> float t).
+def spaced_timesteps(n, section_counts):
+    """Sorted base-chain timesteps kept by `timestep_respacing` (respace.py:7-60): the base chain of n steps is cut into
+    len(section_counts) near-equal sections and section i keeps section_counts[i] evenly strided steps;
+    'ddimK' = the unique integer stride that yields exactly K steps."""
+    if isinstance(section_counts, str):
+        if section_counts.startswith("ddim"):
+            want = int(section_counts[4:])
+            for stride in range(1, n):
+                if len(range(0, n, stride)) == want:
+                    return list(range(0, n, stride))
+            raise ValueError(f"cannot create exactly {n} steps with an integer stride")
+        section_counts = [int(c) for c in section_counts.split(",")]
+    q, r = divmod(n, len(section_counts))
+    kept, first = set(), 0
+    for i, count in enumerate(section_counts):
+        size = q + (1 if i < r else 0)
+        if size < count:
+            raise ValueError(f"cannot divide section of {size} steps into {count}")
+        stride = 1 if count <= 1 else (size - 1) / (count - 1)
+        pos = 0.0
+        for _ in range(count):
+            kept.add(first + round(pos))
+            pos += stride
+        first += size
+    return sorted(kept)
+
+
+def named_betas64(noise_schedule, n):
+    """get_named_beta_schedule (gaussian_diffusion.py:26-73): 'linear' (Ho et al., rescaled to n steps) or 'cosine'
+    (betas from alpha_bar(t) = cos^2((t + 0.008) / 1.008 * pi / 2), capped at 0.999)."""
+    if noise_schedule == "linear":
+        return _linear_betas64(n)
+    if noise_schedule == "cosine":
+        import math
+        bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731
+        return np.array([min(1 - bar((i + 1) / n) / bar(i / n), 0.999) for i in range(n)], dtype=np.float64)
+    raise NotImplementedError(f"unknown beta schedule: {noise_schedule}")
+
+
+class GuidedChain:
+    """The float64 tables of the reference's SpacedDiffusion (respace.py:63-99 over gaussian_diffusion.py:119-180) for
+    (diffusion_steps, noise_schedule, timestep_respacing, rescale_timesteps); '' or None respacing = the full chain.
+    Held to the reference's own create_gaussian_diffusion by tests/golden/guided_schedules.npz."""
+
+    def __init__(self, n=1000, noise_schedule="linear", timestep_respacing="", rescale_timesteps=True):
+        ac_base = np.cumprod(1.0 - named_betas64(noise_schedule, n), axis=0)
+        keep = spaced_timesteps(n, timestep_respacing if timestep_respacing else [n])
+        betas, last = [], 1.0
+        for i in keep:                                         # SpacedDiffusion.__init__, respace.py:76-84
+            betas.append(1 - ac_base[i] / last)
+            last = ac_base[i]
+        self.n_base, self.rescale = n, bool(rescale_timesteps)
+        self.timestep_map = np.array(keep, dtype=np.int64)
+        self.betas = betas = np.array(betas, dtype=np.float64)
+        alphas = 1.0 - betas
+        self.ac = ac = np.cumprod(alphas, axis=0)
+        ac_prev = np.append(1.0, ac[:-1])
+        self.sqrt_recip_ac, self.sqrt_recipm1_ac = np.sqrt(1.0 / ac), np.sqrt(1.0 / ac - 1)
+        post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
+        self.post_logvar_clipped = np.log(np.append(post_var[1], post_var[1:]))
+        self.c1 = betas * np.sqrt(ac_prev) / (1.0 - ac)
+        self.c2 = (1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac)
+        self.num_timesteps = len(betas)
+
+    def model_timesteps(self, idx):
+        """What the UNet is conditioned on at chain index idx: _WrappedModel.__call__ (respace.py:127-136)."""
+        ts = self.timestep_map[idx].astype(np.float32)
+        return ts * np.float32(1000.0 / self.n_base) if self.rescale else ts
+
+
+def guided_tables(t_levels, n=1000, noise_schedule="linear", timestep_respacing="", rescale_timesteps=True):
+    """Learned-range p_sample of guided_diffusion for chain indices t_levels-1 ... 0
+    (runners/diffpure_guided.py:59-75; gaussian_diffusion.py:119-180,240-334,403-447; respace.py:63-136: betas re-derived
+    from the kept cumulative products, the model conditioned on the mapped -- and, by default, rescaled -- timestep).
     coef row: [sqrt(1/ac), sqrt(1/ac - 1), post_mean_coef1, post_mean_coef2, log beta, post_logvar_clipped, t != 0, 0]."""
-    base = _linear_betas64(n)
-    ac_base = np.cumprod(1.0 - base, axis=0)
-    betas, last = [], 1.0
-    for a in ac_base:                                          # SpacedDiffusion.__init__, respace.py:76-84
-        betas.append(1 - a / last)
-        last = a
-    betas = np.array(betas, dtype=np.float64)
-    alphas = 1.0 - betas
-    ac = np.cumprod(alphas, axis=0)
-    ac_prev = np.append(1.0, ac[:-1])
-    post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
-    post_logvar = np.log(np.append(post_var[1], post_var[1:]))
-    c1 = betas * np.sqrt(ac_prev) / (1.0 - ac)
-    c2 = (1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac)
+    ch = GuidedChain(n, noise_schedule, timestep_respacing, rescale_timesteps)
+    if not 0 < t_levels <= ch.num_timesteps:
+        raise ValueError(f"t = {t_levels} outside the {ch.num_timesteps}-step chain")
     idx = np.arange(t_levels - 1, -1, -1)
-    coef = np.stack([np.sqrt(1.0 / ac)[idx], np.sqrt(1.0 / ac - 1)[idx], c1[idx], c2[idx], np.log(betas)[idx],
-                     post_logvar[idx], (idx != 0).astype(np.float64), np.zeros(len(idx))], 1).astype(np.float32)
-    cond = idx.astype(np.float32) * np.float32(1000.0 / n)     # _WrappedModel, respace.py:131-136
+    coef = np.stack([ch.sqrt_recip_ac[idx], ch.sqrt_recipm1_ac[idx], ch.c1[idx], ch.c2[idx], np.log(ch.betas)[idx],
+                     ch.post_logvar_clipped[idx], (idx != 0).astype(np.float64), np.zeros(len(idx))], 1).astype(np.float32)
+    cond = ch.model_timesteps(idx)
     # forward diffusion uses the fp32 copy of the betas (diffpure_guided.py:39,61-62)
-    a32 = (1 - torch.from_numpy(betas).float()).cumprod(dim=0)
+    a32 = (1 - torch.from_numpy(ch.betas).float()).cumprod(dim=0)
     return cond, coef, float(a32[t_levels - 1].sqrt()), float((1.0 - a32[t_levels - 1]).sqrt())
 
 

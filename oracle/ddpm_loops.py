@@ -19,15 +19,57 @@ def _extract(arr, t, shape):
     return res.expand(shape)
 
 
-class GuidedTables:
-    def __init__(self, n=1000):
+def _kept_steps(n, spec):
+    """respace.py:7-60 (space_timesteps): which base timesteps a `timestep_respacing` spec keeps, ascending."""
+    if not spec:
+        return list(range(n))
+    if isinstance(spec, str) and spec.startswith("ddim"):
+        k = int(spec[len("ddim"):])
+        hits = [st for st in range(1, n) if len(range(0, n, st)) == k]
+        if not hits:
+            raise ValueError("no integer stride gives that many steps")
+        return list(range(0, n, hits[0]))
+    counts = [int(v) for v in spec.split(",")] if isinstance(spec, str) else list(spec)
+    out, start = [], 0
+    for i, cnt in enumerate(counts):
+        size = n // len(counts) + (1 if i < n % len(counts) else 0)
+        if size < cnt:
+            raise ValueError("section too small")
+        frac = 1 if cnt <= 1 else (size - 1) / (cnt - 1)
+        out += [start + round(c) for c in _strided(cnt, frac)]
+        start += size
+    return sorted(set(out))
+
+
+def _strided(cnt, frac):
+    cur = 0.0
+    for _ in range(cnt):       # accumulated, not multiplied: the rounding of `cur` is the reference's (respace.py:53-57)
+        yield cur
+        cur += frac
+
+
+def _base_betas(name, n):
+    """gaussian_diffusion.py:26-73."""
+    if name == "linear":
         scale = 1000 / n
-        base = np.linspace(scale * 0.0001, scale * 0.02, n, dtype=np.float64)      # gaussian_diffusion.py:35-43
-        ac_base = np.cumprod(1.0 - base, axis=0)
+        return np.linspace(scale * 0.0001, scale * 0.02, n, dtype=np.float64)
+    if name == "cosine":
+        import math
+        f = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731
+        return np.array([min(1 - f((i + 1) / n) / f(i / n), 0.999) for i in range(n)])
+    raise NotImplementedError(name)
+
+
+class GuidedTables:
+    """SpacedDiffusion's tables (respace.py:63-99 on gaussian_diffusion.py:119-180); defaults = configs/imagenet.yml."""
+
+    def __init__(self, n=1000, noise_schedule="linear", timestep_respacing="", rescale_timesteps=True):
+        ac_base = np.cumprod(1.0 - _base_betas(noise_schedule, n), axis=0)
+        self.timestep_map = _kept_steps(n, timestep_respacing)
         new_betas, last = [], 1.0
-        for a in ac_base:                                                            # respace.py:76-84
-            new_betas.append(1 - a / last)
-            last = a
+        for i in self.timestep_map:                                                  # respace.py:76-84
+            new_betas.append(1 - ac_base[i] / last)
+            last = ac_base[i]
         b = np.array(new_betas, dtype=np.float64)
         self.betas = b
         alphas = 1.0 - b
@@ -40,13 +82,15 @@ class GuidedTables:
         self.c1 = b * np.sqrt(self.ac_prev) / (1.0 - self.ac)
         self.c2 = (1.0 - self.ac_prev) * np.sqrt(alphas) / (1.0 - self.ac)
         self.n = n
+        self.rescale = rescale_timesteps
 
 
 def guided_p_sample(unet, tab, x, i, z):
     """One reverse step at integer timestep i for the whole batch."""
     B = x.shape[0]
     t = torch.full((B,), i, dtype=torch.long)
-    out = unet(x, t.float() * (1000.0 / tab.n))                                     # respace.py:131-136
+    ts = torch.tensor(tab.timestep_map, dtype=torch.long)[t]                        # respace.py:131-136
+    out = unet(x, ts.float() * (1000.0 / tab.n) if tab.rescale else ts.float())
     eps, var = torch.split(out, 3, dim=1)                                           # L272
     min_log = _extract(tab.post_logvar_clipped, t, x.shape)
     max_log = _extract(np.log(tab.betas), t, x.shape)
@@ -58,8 +102,8 @@ def guided_p_sample(unet, tab, x, i, z):
     return mean + nonzero * torch.exp(0.5 * logvar) * z                             # L438-446
 
 
-def purify_guided(unet, x0, t_levels, init_noise, step_noise, n=1000):
-    tab = GuidedTables(n)
+def purify_guided(unet, x0, t_levels, init_noise, step_noise, n=1000, **chain):
+    tab = GuidedTables(n, **chain)
     betas32 = torch.from_numpy(tab.betas).float()
     a = (1 - betas32).cumprod(dim=0)
     x = x0 * a[t_levels - 1].sqrt() + init_noise * (1.0 - a[t_levels - 1]).sqrt()   # diffpure_guided.py:60-62

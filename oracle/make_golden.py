@@ -164,7 +164,7 @@ def golden_adm_and_celeba():
     print("celeba tiny |y|", y.abs().mean().item())
 
 
-if __name__ == "__main__" and not ({"--siblings", "--adm-vpsde", "--checkpoint-keys"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--siblings", "--adm-vpsde", "--checkpoint-keys", "--guided-schedules"} & set(sys.argv)):
     if "--adm-celeba" not in sys.argv:
         main()
     if "--ncsnpp" not in sys.argv:
@@ -269,3 +269,62 @@ def golden_checkpoint_keys():
 
 if __name__ == "__main__" and "--checkpoint-keys" in sys.argv:
     golden_checkpoint_keys()
+
+
+GUIDED_SCHEDULE_CASES = [  # (diffusion_steps, noise_schedule, timestep_respacing, rescale_timesteps)
+    (1000, "linear", "1000", True),      # configs/imagenet.yml
+    (1000, "linear", "250", True),
+    (1000, "linear", "100,50,25", False),
+    (1000, "cosine", "ddim50", True),
+    (500, "cosine", "", False),
+]
+
+
+def golden_guided_schedules():
+    """The reference's SpacedDiffusion tables (guided_diffusion/script_util.py:create_gaussian_diffusion ->
+    respace.py:63-99) for non-default timestep_respacing / noise_schedule / rescale_timesteps, and one learned-range
+    p_sample chain of the reduced ADM under timestep_respacing='100,50,25' (runners/diffpure_guided.py:59-75)."""
+    ref_import.install()
+    from guided_diffusion.script_util import create_gaussian_diffusion, create_model_and_diffusion, \
+        model_and_diffusion_defaults
+    from oracle import adm as A
+    torch.set_grad_enabled(False)
+    out = {}
+    for ci, (n, ns, tr, rs) in enumerate(GUIDED_SCHEDULE_CASES):
+        d = create_gaussian_diffusion(steps=n, learn_sigma=True, noise_schedule=ns, timestep_respacing=tr,
+                                      rescale_timesteps=rs)
+        out[f"c{ci}_timestep_map"] = np.array(d.timestep_map, dtype=np.int64)
+        for k in ("betas", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                  "posterior_mean_coef2", "posterior_log_variance_clipped"):
+            out[f"c{ci}_{k}"] = np.asarray(getattr(d, k), dtype=np.float64)
+    # chain: reduced ADM through the reference's own SpacedDiffusion.p_sample (model wrapped by _WrappedModel)
+    cfg = ref_import.load_config("imagenet.yml")
+    mc = model_and_diffusion_defaults()
+    mc.update(vars(cfg.model))
+    mc.update(num_channels=64, image_size=64, num_res_blocks=1, attention_resolutions="32,16,8", use_fp16=False,
+              timestep_respacing="100,50,25")
+    m, diffusion = create_model_and_diffusion(**mc)
+    m.eval()
+    oc = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    m.load_state_dict(weights.make_state_dict(A.param_shapes(oc), seed=5))
+    t_levels, B, S = 3, 2, 64
+    g = torch.Generator().manual_seed(700)
+    x0 = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    e0 = torch.randn(B, 3, S, S, generator=g)
+    betas = torch.from_numpy(diffusion.betas).float()
+    a = (1 - betas).cumprod(dim=0)
+    xx = x0 * a[t_levels - 1].sqrt() + e0 * (1.0 - a[t_levels - 1]).sqrt()
+    torch.manual_seed(79)
+    for i in reversed(range(t_levels)):
+        xx = diffusion.p_sample(m, xx, torch.tensor([i] * B), clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                model_kwargs=None)["sample"]
+    torch.manual_seed(79)
+    z = torch.stack([torch.randn_like(x0) for _ in range(t_levels)])
+    np.savez_compressed(os.path.join(OUT, "guided_schedules.npz"), chain_respacing="100,50,25", chain_t_levels=t_levels,
+                        chain_seed=5, chain_input_seed=700, chain_z=z.numpy(), chain_out=xx.numpy(), **out)
+    print("guided schedules:", len(GUIDED_SCHEDULE_CASES), "cases; respaced chain |x|", xx.abs().mean().item(),
+          "model timesteps", [diffusion.timestep_map[i] for i in reversed(range(t_levels))])
+
+
+if __name__ == "__main__" and "--guided-schedules" in sys.argv:
+    golden_guided_schedules()

@@ -7,7 +7,7 @@ import torch
 
 from diffpure_b200 import lowering_adm as LA, lowering_ddpm as LD, schedule
 from oracle import adm as A, ddpm_loops as OL, ddpm_unet as D, weights
-from golden_inputs import adm_vpsde_inputs
+from golden_inputs import adm_vpsde_inputs, respaced_chain_inputs
 from oracle import sde as OS
 from program_interp import Interp
 
@@ -124,3 +124,44 @@ def test_adm_on_the_vpsde_path_oracle_and_tables_match_reference_golden():
     # ... and the 150-step ImageNet grid starts at 149 with one duplicate
     c150, _ = schedule.vpsde_tables(150, "guided_diffusion")
     assert len(c150) == 150 and c150[0] == 149 and c150[-1] == 1 and len(set(c150.tolist())) == 149
+
+
+GUIDED_CASES = [(1000, "linear", "1000", True), (1000, "linear", "250", True), (1000, "linear", "100,50,25", False),
+                (1000, "cosine", "ddim50", True), (500, "cosine", "", False)]   # oracle/make_golden.py:GUIDED_SCHEDULE_CASES
+
+
+def test_respaced_guided_chains_match_reference_golden():
+    """timestep_respacing / noise_schedule / rescale_timesteps (configs/imagenet.yml invites changing them): the product's
+    host tables (schedule.GuidedChain) and the oracle's (ddpm_loops.GuidedTables) are bit-identical to the reference's
+    create_gaussian_diffusion -> SpacedDiffusion (fixture tests/golden/guided_schedules.npz), and the oracle chain under
+    '100,50,25' reproduces the reference's own p_sample chain."""
+    d = np.load(os.path.join(G, "guided_schedules.npz"))
+    names = ("betas", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+             "posterior_mean_coef2", "posterior_log_variance_clipped")
+    for ci, (n, ns, tr, rs) in enumerate(GUIDED_CASES):
+        ch = schedule.GuidedChain(n, ns, tr, rs)
+        tab = OL.GuidedTables(n, ns, tr, rs)
+        assert ch.timestep_map.tolist() == d[f"c{ci}_timestep_map"].tolist() == list(tab.timestep_map)
+        mine = (ch.betas, ch.sqrt_recip_ac, ch.sqrt_recipm1_ac, ch.c1, ch.c2, ch.post_logvar_clipped)
+        orac = (tab.betas, tab.sqrt_recip_ac, tab.sqrt_recipm1_ac, tab.c1, tab.c2, tab.post_logvar_clipped)
+        for k, a, b in zip(names, mine, orac):
+            assert np.array_equal(a, d[f"c{ci}_{k}"]) and np.array_equal(b, d[f"c{ci}_{k}"]), (ci, k)
+        # the device tables: rows t-1 ... 0 of the chain, the UNet conditioned on the mapped (and rescaled) timestep
+        t = min(7, ch.num_timesteps)
+        cond, coef, sx, se = schedule.guided_tables(t, n, ns, tr, rs)
+        idx = np.arange(t - 1, -1, -1)
+        want = ch.timestep_map[idx].astype(np.float32) * (np.float32(1000.0 / n) if rs else np.float32(1))
+        assert np.array_equal(cond, want) and coef.shape == (t, 8)
+        assert np.array_equal(coef[:, 4], np.log(d[f"c{ci}_betas"])[idx].astype(np.float32))
+    # chain through the oracle ADM
+    sd = weights.make_state_dict(A.param_shapes(ADM_TINY), seed=int(d["chain_seed"]))
+    unet = lambda x, t: A.forward(ADM_TINY, sd, x, t)  # noqa: E731
+    x0, e0 = respaced_chain_inputs(int(d["chain_input_seed"]))
+    out = OL.purify_guided(unet, x0, int(d["chain_t_levels"]), e0, torch.from_numpy(d["chain_z"]),
+                           timestep_respacing=str(d["chain_respacing"]))
+    assert (out - torch.from_numpy(d["chain_out"])).abs().max().item() < 1e-4
+    # ... and it is a different chain from the full one (the fixture would not notice a ignored respacing otherwise)
+    full = OL.purify_guided(unet, x0, int(d["chain_t_levels"]), e0, torch.from_numpy(d["chain_z"]))
+    assert (full - torch.from_numpy(d["chain_out"])).abs().max().item() > 1e-2
+    with np.testing.assert_raises(ValueError):
+        schedule.guided_tables(51, 1000, "cosine", "ddim50")

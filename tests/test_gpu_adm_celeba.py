@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_inputs import ADM_TINY_REF_CONFIG, adm_vpsde_inputs
+from golden_inputs import ADM_TINY_REF_CONFIG, adm_vpsde_inputs, respaced_chain_inputs
 from oracle import adm as A, ddpm_unet as D, sde as OS, weights
 
 pytestmark = pytest.mark.gpu
@@ -89,6 +89,25 @@ def test_guided_and_ddpm_runner_api():
         Diffusion(args, SimpleNamespace(data=SimpleNamespace(dataset="LSUN"), model=config.model,
                                         diffusion=config.diffusion), device=torch.device("cuda:0"), state_dict={})
     r.model.release()
+
+
+def test_guided_runner_respaced_chain_golden():
+    """config.model.timestep_respacing = '100,50,25': GuidedDiffusion on the engine vs the chain the reference's own
+    SpacedDiffusion.p_sample produced (tests/golden/guided_schedules.npz; oracle/make_golden.py:golden_guided_schedules)."""
+    from diffpure_b200.runners.diffpure_guided import GuidedDiffusion
+    d = np.load(os.path.join(G, "guided_schedules.npz"))
+    mc = dict(ADM_TINY_REF_CONFIG, timestep_respacing=str(d["chain_respacing"]))
+    args = SimpleNamespace(t=int(d["chain_t_levels"]), sample_step=1, log_dir="/tmp/dp_test_logs", save_images=False)
+    config = SimpleNamespace(data=SimpleNamespace(dataset="ImageNet"), model=SimpleNamespace(**mc))
+    acfg = A.tiny_cfg(64, 64, (1, 2, 3, 4), 1, (32, 16, 8))
+    r = GuidedDiffusion(args, config, device=torch.device("cuda:0"),
+                        state_dict=weights.make_state_dict(A.param_shapes(acfg), seed=int(d["chain_seed"])))
+    x0, e0 = respaced_chain_inputs(int(d["chain_input_seed"]))
+    out = r.image_editing_sample(x0.cuda(), bs_id=3, tag="rs", init_noise=e0.cuda(),
+                                 step_noise=torch.from_numpy(d["chain_z"]).cuda())
+    r.model.release()
+    want = torch.from_numpy(d["chain_out"])
+    assert rel(out.cpu(), want) < TOL_TRAJ, rel(out.cpu(), want)
 
 
 @pytest.mark.parametrize("which", ["adm", "celeba"])

@@ -223,6 +223,14 @@ def test_guided_and_celeba_runners_flow():
     x, e, z = _data(steps=4, seed=9)
     out = r.image_editing_sample(x, bs_id=5, tag="g", init_noise=e, step_noise=z)
     assert torch.allclose(out, OD.purify_guided(net6, x, 4, e, z), atol=2e-5)
+    # timestep_respacing / noise_schedule / rescale_timesteps build the reference's SpacedDiffusion chain (respace.py:63-136)
+    config.model.timestep_respacing, config.model.noise_schedule, config.model.rescale_timesteps = "100,50,25", "cosine", False
+    r = GuidedDiffusion(args, config, device="cpu", state_dict=weights.make_state_dict(A.param_shapes(acfg), seed=0))
+    r.model = net6
+    assert r.num_timesteps == 175 and r.diffusion.timestep_map[:4] == [0, 3, 7, 10] and len(r.betas) == 175
+    out = r.image_editing_sample(x, bs_id=5, tag="g", init_noise=e, step_noise=z)
+    ref = OD.purify_guided(net6, x, 4, e, z, noise_schedule="cosine", timestep_respacing="100,50,25", rescale_timesteps=False)
+    assert torch.allclose(out, ref, atol=2e-5) and not torch.allclose(ref, OD.purify_guided(net6, x, 4, e, z), atol=1e-3)
 
     ccfg = D.tiny_cfg(32, 64, (1, 2, 2), 1, (16,))
     config = SimpleNamespace(data=SimpleNamespace(dataset="CelebA_HQ", image_size=32),
