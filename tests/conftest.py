@@ -11,6 +11,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 GPU (run with -m gpu under gpurun)")
+    # The oracle sides run on the host: torch's default (one thread per core) oversubscribes the GPU boxes' many-core
+    # hosts badly on these small convolutions -- the same observation as bench.py:_best_cpu_threads.
+    try:
+        import torch
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:
+        pass
 
 
 def _has_gpu():

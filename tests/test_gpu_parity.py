@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 import torch
 
+from golden_inputs import cifar_pair_eval_inputs, cifar_traj100_inputs, cifar_traj30_inputs
 from oracle import ncsnpp as O, sde as OS, weights
 
 pytestmark = pytest.mark.gpu
@@ -113,25 +114,14 @@ def test_tiny_eval_and_loop_golden(name, cfg):
 
 
 def test_full_model_trajectory_vs_oracle():
-    """CIFAR-10 DDPM++ (106 M parameters), 30 Euler-Maruyama steps from t*=0.1 with injected noise."""
+    """CIFAR-10 DDPM++ (106 M parameters), 30 Euler-Maruyama steps from t*=0.1 with injected noise vs the oracle loop
+    (precomputed: tests/golden/fullsize_oracle.npz, oracle/make_fullsize_golden.py)."""
+    import fullsize as F
     from diffpure_b200 import schedule
-    cfg = O.CIFAR10_CFG
-    sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
-    g = torch.Generator().manual_seed(5)
+    cfg, sd = O.CIFAR10_CFG, F.state_dict("cifar")
     B, t_star, steps = 2, 100, 30
-    x0 = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
-    e0 = torch.randn(B, 3, 32, 32, generator=g)
-    z = torch.randn(steps, B, 3, 32, 32, generator=g)
-    # oracle: first `steps` steps of the 100-step grid
-    grid = OS.time_grid(t_star)
-    x = OS.forward_diffuse(x0, e0, t_star)
-    unet = lambda xx, tt: O.forward(cfg, sd, xx, tt)  # noqa: E731
-    with torch.no_grad():
-        for k in range(steps):
-            t, tn = grid[k], grid[k + 1]
-            h = tn - t
-            x = x + OS.rev_vpsde_f(unet, "score_sde", t, x) * h + \
-                OS.rev_vpsde_g(t, B)[:, None, None, None] * z[k] * torch.sqrt(h)
+    x0, e0, z = cifar_traj30_inputs()
+    x = F.oracle_results()["cifar_traj30"]
     cond, coef = schedule.vpsde_tables(t_star)
     sx, se = schedule.vpsde_forward_scales(t_star)
     eng = engine_for(cfg, sd, B)
@@ -143,13 +133,10 @@ def test_full_model_trajectory_vs_oracle():
 def test_pair_tiles_in_the_full_model_match_single_cta_tiles_and_oracle():
     """At B=96 the 32x32 and 16x16 convolutions of the CIFAR-10 model run on CTA-pair (cta_group::2) tiles, at B=2 mostly on
     single-CTA tiles: the first two samples must agree with the B=2 engine and with the oracle."""
-    cfg = O.CIFAR10_CFG
-    sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
-    g = torch.Generator().manual_seed(15)
-    x = torch.rand(96, 3, 32, 32, generator=g) * 2 - 1
-    labels = torch.full((96,), 37.0)
-    with torch.no_grad():
-        y = O.forward(cfg, sd, x[:2], labels[:2])
+    import fullsize as F
+    cfg, sd = O.CIFAR10_CFG, F.state_dict("cifar")
+    x, labels = cifar_pair_eval_inputs()
+    y = F.oracle_results()["cifar_pair_eval"]          # the oracle's evaluation of the first two samples, precomputed
     e96 = engine_for(cfg, sd, 96)
     y96 = e96.unet_forward(x.cuda(), labels.cuda()).cpu()
     n96 = e96.pair_gemms
@@ -222,20 +209,15 @@ def test_full_size_identity_update_property():
 def test_full_model_100_step_trajectory_at_pair_tile_batch():
     """The benchmarked loop shape: all 100 Euler-Maruyama steps from t*=0.1 on the full CIFAR-10 model at B=96 (the 32x32 and
     16x16 convolutions run on CTA-pair tiles, as at B=512) with injected noise; the first two samples are held to the
-    oracle loop. The measured rel-L2 is reported, not just bounded (stated bound: 5e-3 for K <= 100)."""
+    oracle loop (precomputed: tests/golden/fullsize_oracle.npz). The measured rel-L2 is reported, not just bounded (stated bound: 5e-3 for K <= 100)."""
+    import fullsize as F
     from diffpure_b200 import schedule
-    cfg = O.CIFAR10_CFG
-    sd = weights.make_state_dict(O.param_shapes(cfg), seed=0)
-    g = torch.Generator().manual_seed(6)
+    cfg, sd = O.CIFAR10_CFG, F.state_dict("cifar")
     B, t_star = 96, 100
     steps = OS.num_steps(t_star)
     assert steps == 100
-    x0 = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
-    e0 = torch.randn(B, 3, 32, 32, generator=g)
-    z = torch.randn(steps, B, 3, 32, 32, generator=g)
-    torch.set_num_threads(min(16, os.cpu_count() or 1))
-    with torch.no_grad():
-        ref = OS.purify_sde(lambda xx, tt: O.forward(cfg, sd, xx, tt), x0[:2], t_star, e0[:2], z[:, :2])
+    x0, e0, z = cifar_traj100_inputs()
+    ref = F.oracle_results()["cifar_traj100"]          # OS.purify_sde of the first two samples, precomputed
     cond, coef = schedule.vpsde_tables(t_star)
     sx, se = schedule.vpsde_forward_scales(t_star)
     eng = engine_for(cfg, sd, B)
