@@ -537,6 +537,8 @@ int dp_op_gemm(dp_engine* e, const dp_gemm_desc* d) {
     p.gn_gamma = d->gn_gamma; p.gn_beta = d->gn_beta;
     p.gn_cpg = d->N / d->gn_groups; p.gn_hw = hw; p.gn_eps = d->gn_eps; p.gn_silu = d->gn_silu;
     p.tpg = gn_tpg; p.acc_stages = gn_stages;
+    static const int gn_p1 = [] { const char* v = std::getenv("DP_GN_P1"); return v ? std::atoi(v) : 1; }();
+    p.gn_p1 = gn_p1;
     if (gn_super) {
       constexpr size_t kSlots = 128, kData = kSlots * 2 * 4 * 64 * 2 * sizeof(float), kFlags = kSlots * 4 * 8;
       if (!e->xg) {

@@ -19,6 +19,7 @@
 #include "dp_rng.cuh"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace dp {
 

@@ -98,6 +98,7 @@ struct GemmParams {
   float gn_eps;
   int gn_silu;
   int gn_xchg;            // 1: a sample spans both CTAs of the pair (upc == 1)
+  int gn_p1;              // 1: resident variant, H*W >= 128: pass 1 keeps group sums per lane (no smem transpose); 0: per-channel pass
   // super-pair exchange (upc == 2), engine-owned, shared by all launches of a stream:
   float* xg_data;         // [super-pairs][2 parities][4 CTAs][BN / cpg groups][2] partial (sum, sum of squares)
   unsigned long long* xg_flag;   // [super-pairs][4 CTAs]: token of the last unit each CTA published (64-bit: never wraps)

@@ -109,6 +109,7 @@ static void run_conv(const ConvCase& cs) {
     p.gn_out = cs.gn == 2 ? d_gn : d_outb;
     p.gn_gamma = d_gamma; p.gn_beta = d_beta;
     p.gn_cpg = N / groups; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
+    p.gn_p1 = getenv("DP_GN_P1") ? atoi(getenv("DP_GN_P1")) : 1;   // group-sum pass 1 (default) / per-channel pass 1
     const bool super_pair = strstr(cs.name, "super-pair") != nullptr;
     if (H * W == 1024 && !super_pair) { p.tpg = 4; p.acc_stages = 4; }  // the sample's four tiles resident in one pair
     if (cs.bn == 128) p.acc_stages = 4;
@@ -395,6 +396,7 @@ static void run_perf(int B, int H, int W, int C0, int taps, int N, int resid, in
     p.out_f32 = nullptr; p.out_bf16 = nullptr; p.stats = nullptr;
     p.gn_out = reinterpret_cast<__nv_bfloat16*>(d_out);
     p.gn_gamma = d_bias; p.gn_beta = d_bias; p.gn_cpg = N / 32; p.gn_hw = H * W; p.gn_eps = 1e-6f; p.gn_silu = 1;
+    p.gn_p1 = getenv("DP_GN_P1") ? atoi(getenv("DP_GN_P1")) : 1;
     const bool super_pair = getenv("DP_GN_UPC") && atoi(getenv("DP_GN_UPC")) == 2;
     if (H * W == 1024 && !super_pair) { p.tpg = 4; p.acc_stages = 4; }
     if (H * W == 1024 && super_pair) {
@@ -439,11 +441,13 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, devid));
   num_sms = prop.multiProcessorCount;
+  if (getenv("DP_SELFTEST_SMS")) num_sms = atoi(getenv("DP_SELFTEST_SMS"));   // a smaller grid: several work units per CTA (pair)
   printf("device %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, num_sms);
   int e = dp::gemm_init();
   if (e) { printf("gemm_init failed %d\n", e); return 2; }
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   const bool pair_only = argc > 1 && !strcmp(argv[1], "pair");
+  const bool gn_only = argc > 1 && !strcmp(argv[1], "gn");      // the fused-GroupNorm cases only (A/B of DP_GN_P1)
   if (argc > 8 && !strcmp(argv[1], "perf")) {
     run_perf(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]), argc > 9 ? atoi(argv[9]) : 0,
              argc > 10 ? atoi(argv[10]) : 1);
@@ -503,10 +507,11 @@ int main(int argc, char** argv) {
   for (int i = 0; i < ncases; ++i) {
     if (quick && i >= 4) break;
     if (pair_only && cases[i].cg != 2) continue;
+    if (gn_only && !cases[i].gn) continue;
     run_conv(cases[i]);
   }
-  if (!pair_only) run_attention(3, 256, 256, 256);
-  if (!quick && !pair_only) run_attention(2, 128, 512, 128);
+  if (!pair_only && !gn_only) run_attention(3, 256, 256, 256);
+  if (!quick && !pair_only && !gn_only) run_attention(2, 128, 512, 128);
   printf("selftest_gemm: %d failure(s)\n", failures);
   return failures ? 1 : 0;
 }

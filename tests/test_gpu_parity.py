@@ -145,6 +145,8 @@ def test_pair_tiles_in_the_full_model_match_single_cta_tiles_and_oracle():
     y2 = e2.unet_forward(x[:2].cuda(), labels[:2].cuda()).cpu()
     n2 = e2.pair_gemms
     e2.close()
+    print(f"pair tiles: {n96} / {n2} pair GEMMs; rel-L2 B=96 vs oracle {rel(y96[:2], y):.3e}, B=2 vs oracle {rel(y2, y):.3e}, "
+          f"B=96 vs B=2 {rel(y96[:2], y2):.3e}")
     assert n96 >= 40 and n2 < n96, (n96, n2)   # at B=2 only the fused-GroupNorm GEMMs (whole sample per pair) use pairs
     assert rel(y96[:2], y) < TOL_EVAL, rel(y96[:2], y)
     assert rel(y96[:2], y2) < 1e-3, rel(y96[:2], y2)      # same arithmetic, different tiling
